@@ -1,0 +1,238 @@
+/*
+ * rqcd.h -- C ABI of the B200-native batched motion-primitive generator and
+ * convex-obstacle collision checker.
+ *
+ * This is the drop-in boundary for ONE path of
+ * nlbucki/RapidQuadcopterCollisionDetection: the per-trial body of its two
+ * drivers (test/PerformanceEval.cpp:140-182, test/ForestPerformanceEval.cpp:177-225),
+ * i.e.  RapidTrajectoryGenerator::Generate -> GetTrajectory ->
+ * CollisionChecker::CollisionCheck(obstacle, minTimeSection).
+ * The reference has no FFI of its own (it is a C++ class library,
+ * src/CMakeLists.txt:1-3); each entry point below names the reference
+ * interface it replaces.  The C++ facade in include/rqcd/ keeps the reference's
+ * class names and calls only these functions.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; the caller owns every buffer.
+ *  - every function returns an rqcd_status; nothing throws, nothing aborts.
+ *  - all arithmetic is IEEE-754 binary64, evaluated in the reference's
+ *    operation order without FMA contraction ("exact" mode).
+ *  - there is no CPU fallback: without a CUDA device rqcd_create fails with
+ *    RQCD_ERR_NO_DEVICE and nothing else can be called.
+ *  - a context is bound to one GPU and one stream; use one context per host
+ *    thread / per rank (one process per GPU under torchrun).
+ */
+#ifndef RQCD_H_
+#define RQCD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RQCD_VERSION_MAJOR 0
+#define RQCD_VERSION_MINOR 1
+
+typedef enum rqcd_status {
+  RQCD_OK = 0,
+  RQCD_ERR_INVALID_ARG = 1, /* null pointer, n < 0, stride < n, minT <= 0 or NaN, bad obstacle */
+  RQCD_ERR_CUDA = 2,        /* a CUDA runtime call failed; see rqcd_last_error */
+  RQCD_ERR_NO_DEVICE = 3,   /* no usable sm_100 device: there is no CPU fallback */
+  RQCD_ERR_DEPTH_CAP = 4,   /* some pair hit the internal interval-stack cap (verdict 3) */
+  RQCD_ERR_NOMEM = 5,
+  RQCD_ERR_UNSUPPORTED = 6  /* e.g. obstacle type outside the closed set {sphere, prism} */
+} rqcd_status;
+
+/* Verdict of one check. Values 0..2 are the reference's
+ * CollisionChecker::CollisionResult (include/RapidCollisionDetection/CollisionChecker.hpp:33-37).
+ * 3 never occurs unless (t_end - t_start)/minT exceeds 2^RQCD_MAX_DEPTH. */
+typedef enum rqcd_verdict {
+  RQCD_NO_COLLISION = 0,
+  RQCD_COLLISION = 1,
+  RQCD_INDETERMINABLE = 2,
+  RQCD_DEPTH_CAP = 3
+} rqcd_verdict;
+
+/* RapidTrajectoryGenerator::InputFeasibilityResult
+ * (include/RapidQuadcopterTrajectories/RapidTrajectoryGenerator.hpp:63-69). */
+typedef enum rqcd_input_feasibility {
+  RQCD_INPUT_FEASIBLE = 0,
+  RQCD_INPUT_INDETERMINABLE = 1,
+  RQCD_INPUT_INFEASIBLE_THRUST_HIGH = 2,
+  RQCD_INPUT_INFEASIBLE_THRUST_LOW = 3,
+  RQCD_INPUT_INFEASIBLE_RATES = 4
+} rqcd_input_feasibility;
+
+/* ---- obstacles -----------------------------------------------------------
+ * The reference's open virtual interface CommonMath::ConvexObj
+ * (include/CommonMath/ConvexObj.hpp:61-82) becomes a closed tagged record:
+ * Sphere (include/CommonMath/Sphere.hpp:40-72) or RectPrism
+ * (include/CommonMath/RectPrism.hpp:46-100). */
+typedef enum rqcd_obstacle_type { RQCD_SPHERE = 0, RQCD_RECT_PRISM = 1 } rqcd_obstacle_type;
+
+typedef struct rqcd_obstacle {
+  int32_t type;      /* rqcd_obstacle_type */
+  int32_t moving;    /* 0: static.  1: translates (no rotation) along `motion`; the pair check
+                        is CollisionChecker(traj - motion).CollisionCheck(shape, minT), the
+                        composition of include/CommonMath/Trajectory.hpp:121-128 */
+  double center[3];  /* Sphere::_centerPoint / RectPrism::_centerPoint (for a moving obstacle:
+                        the shape's centre in the frame that moves with `motion`) */
+  double radius;     /* sphere only, > 0 (Sphere.hpp:44) */
+  double side[3];    /* prism only: full side lengths, each > 0 (RectPrism.hpp:52) */
+  double quat[4];    /* prism only: Rotation(a,b,c,d) local->global (Rotation.hpp:42-47) */
+  double motion[18]; /* moving only: quintic coefficients, motion[3*k+dim], k=0 is t^5
+                        (Trajectory.hpp:26-31) */
+  double motion_t_start, motion_t_end; /* moving only: window of `motion` */
+} rqcd_obstacle;
+
+/* ---- trajectories --------------------------------------------------------
+ * Boundary conditions, structure-of-arrays: row r of the matrix starts at
+ * data + r*stride and holds n doubles.  Rows follow the argument order of
+ * RapidTrajectoryGenerator(x0,v0,a0,gravity) + SetGoalPosition/Velocity/
+ * Acceleration + Generate(Tf) (RapidTrajectoryGenerator.hpp:77-114). */
+enum {
+  RQCD_BC_P0 = 0,  /* rows 0..2  : initial position x,y,z */
+  RQCD_BC_V0 = 3,  /* rows 3..5  : initial velocity */
+  RQCD_BC_A0 = 6,  /* rows 6..8  : initial acceleration */
+  RQCD_BC_PF = 9,  /* rows 9..11 : goal position   (ignored where the goal bit is clear) */
+  RQCD_BC_VF = 12, /* rows 12..14: goal velocity */
+  RQCD_BC_AF = 15, /* rows 15..17: goal acceleration */
+  RQCD_BC_TF = 18, /* row 18     : duration Tf */
+  RQCD_BC_ROWS = 19
+};
+
+/* goal_mask bit (3*axis + c): component c (0 pos, 1 vel, 2 acc) of axis is constrained
+ * (SingleAxisTrajectory::SetGoalPosition/Velocity/Acceleration, SingleAxisTrajectory.hpp:39-45).
+ * One mask per batch, as in both reference drivers. */
+#define RQCD_GOAL_POS(axis) (1u << (3 * (axis) + 0))
+#define RQCD_GOAL_VEL(axis) (1u << (3 * (axis) + 1))
+#define RQCD_GOAL_ACC(axis) (1u << (3 * (axis) + 2))
+#define RQCD_GOAL_ALL 0x1FFu
+
+typedef struct rqcd_bc_soa {
+  const double* data; /* RQCD_BC_ROWS rows */
+  int64_t stride;     /* doubles between rows, >= n */
+  uint32_t goal_mask;
+  uint32_t reserved;
+} rqcd_bc_soa;
+
+/* Pre-built quintics (CommonMath::Trajectory, Trajectory.hpp:44-69), structure-of-arrays:
+ * row 3*k+dim (k = 0 is t^5) starts at coeffs + (3*k+dim)*stride. */
+#define RQCD_COEFF_ROWS 18
+typedef struct rqcd_coeff_soa {
+  const double* coeffs;
+  int64_t stride;
+  const double* t_start; /* n doubles, or NULL for 0 */
+  const double* t_end;   /* n doubles, required */
+} rqcd_coeff_soa;
+
+/* ---- results ------------------------------------------------------------- */
+typedef struct rqcd_summary {
+  uint64_t traj_counts[4]; /* trajectories by first-hit verdict (index = rqcd_verdict) */
+  uint64_t pair_counts[4]; /* executed trajectory-obstacle checks by verdict */
+  uint64_t pairs_checked;  /* = sum(pair_counts); n*m unless RQCD_F_EARLY_EXIT */
+  double best_cost;        /* min GetCost() over NoCollision trajectories, +inf if none */
+  int64_t best_index;      /* index_base + local index of that trajectory (lowest on ties), -1 if none */
+} rqcd_summary;
+
+typedef struct rqcd_out {
+  uint8_t* verdict;        /* [n] first obstacle in index order whose check != NoCollision gives
+                              the verdict, else NoCollision (ForestPerformanceEval.cpp:216-225); may be NULL */
+  int32_t* first_obstacle; /* [n] index of that obstacle, -1 if none; may be NULL */
+  uint8_t* verdict_matrix; /* [n*m] row-major per trajectory, every pair's own verdict; may be NULL.
+                              Not allowed together with RQCD_F_EARLY_EXIT */
+  double* cost;            /* [n] RapidTrajectoryGenerator::GetCost(); may be NULL */
+  double* coeffs;          /* RQCD_COEFF_ROWS rows, GetTrajectory() coefficients; may be NULL */
+  int64_t coeff_stride;
+  rqcd_summary* summary;   /* HOST pointer (also with RQCD_F_DEVICE_PTRS); may be NULL. When non-NULL
+                              the call synchronises the context's stream before returning. */
+} rqcd_out;
+
+/* flags */
+#define RQCD_F_DEVICE_PTRS 0x1u /* every data pointer in the in/out structs is a device pointer on the
+                                   context's GPU; the call only enqueues work on the context's stream */
+#define RQCD_F_EARLY_EXIT 0x2u  /* stop each trajectory at its first non-NoCollision obstacle (what the
+                                   Forest driver does); default is all pairs */
+
+#define RQCD_MAX_DEPTH 40       /* interval-stack entries per check */
+
+typedef struct rqcd_ctx rqcd_ctx;
+
+/* ---- context ------------------------------------------------------------- */
+int rqcd_create(rqcd_ctx** ctx, int device);
+void rqcd_destroy(rqcd_ctx* ctx);
+const char* rqcd_strerror(int status);
+const char* rqcd_last_error(const rqcd_ctx* ctx); /* text of the last CUDA failure on this context */
+int rqcd_device_info(const rqcd_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, char* name, size_t name_len);
+
+/* The stream the context launches on (a cudaStream_t). rqcd_set_stream lets the caller supply its
+ * own (e.g. to time with events); pass NULL to go back to the context-owned stream. */
+void* rqcd_get_stream(const rqcd_ctx* ctx);
+int rqcd_set_stream(rqcd_ctx* ctx, void* cuda_stream);
+int rqcd_synchronize(rqcd_ctx* ctx);
+/* Summary of the most recent check launch on this context (synchronises). */
+int rqcd_read_summary(rqcd_ctx* ctx, rqcd_summary* out);
+/* Number of kernels this context has launched since creation. */
+uint64_t rqcd_launch_count(const rqcd_ctx* ctx);
+
+/* Replaces constructing Sphere / RectPrism objects and the vector<shared_ptr<ConvexObj>> the drivers
+ * hold (ForestPerformanceEval.cpp:130-150). Host pointer always. Rotation matrices and half sides are
+ * hoisted here with the reference's expression order (Rotation.hpp:203-220). The set is replicated per
+ * GPU; static and moving obstacles may be mixed. */
+int rqcd_set_obstacles(rqcd_ctx* ctx, const rqcd_obstacle* obstacles, int32_t m);
+int32_t rqcd_num_obstacles(const rqcd_ctx* ctx);
+
+/* ---- the hot path --------------------------------------------------------- */
+
+/* Generate + GetCost + GetTrajectory only (RapidTrajectoryGenerator.cpp:67-72, .hpp:214-241).
+ * Uses out->cost, out->coeffs; other fields ignored. */
+int rqcd_generate(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, uint32_t flags, rqcd_out* out);
+
+/* Fused Generate -> GetTrajectory -> CollisionCheck against the whole obstacle set: the body of the
+ * Forest driver's candidate loop (ForestPerformanceEval.cpp:186-225) for n candidates at once.
+ * index_base is added to local indices in summary.best_index (shard offset). */
+int rqcd_generate_check(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, double min_time_section,
+                        uint32_t flags, int64_t index_base, rqcd_out* out);
+
+/* CollisionChecker(Trajectory).CollisionCheck(obstacle, minTimeSection) for pre-built quintics against
+ * the whole set (CollisionChecker.hpp:40-61, CollisionChecker.cpp:70-193). `cost` (n doubles, may be NULL)
+ * only feeds summary.best_*. */
+int rqcd_check(rqcd_ctx* ctx, const rqcd_coeff_soa* in, const double* cost, int64_t n,
+               double min_time_section, uint32_t flags, int64_t index_base, rqcd_out* out);
+
+/* PerformanceEval shape (PerformanceEval.cpp:140-182): trajectory i against its own sphere i.
+ * spheres: 4 rows (cx, cy, cz, radius) of n doubles at spheres + r*sphere_stride. Only out->verdict,
+ * cost, coeffs, summary are used. */
+int rqcd_generate_check_pairwise(rqcd_ctx* ctx, const rqcd_bc_soa* in, const double* spheres,
+                                 int64_t sphere_stride, int64_t n, double min_time_section,
+                                 uint32_t flags, int64_t index_base, rqcd_out* out);
+
+/* ---- solver unit entry points (test surface of Quartic::solveP3 / solve_quartic,
+ * src/quartic.cpp:39-156). coef: 3 (cubic a,b,c) or 4 (quartic a,b,c,d) rows of n doubles, row stride n.
+ * roots: 3 or 4 rows of n doubles (row stride n); count[n]. Host or device pointers per flags. */
+int rqcd_solve_cubic(rqcd_ctx* ctx, const double* coef, int64_t n, uint32_t flags, double* roots, int32_t* count);
+int rqcd_solve_quartic(rqcd_ctx* ctx, const double* coef, int64_t n, uint32_t flags, double* roots, int32_t* count);
+
+/* ---- multi-GPU plumbing ---------------------------------------------------
+ * Shards are contiguous candidate ranges, one per rank; each rank holds the full obstacle set. The
+ * only exchange is this merge of per-shard summaries (counts add; best = min cost, lowest index on
+ * ties). It is pure host arithmetic so any transport (NCCL all-gather of the 96-byte records via
+ * torch.distributed, MPI, ...) can carry the records. */
+int rqcd_merge_summaries(const rqcd_summary* shards, int32_t n_shards, rqcd_summary* merged);
+
+/* ---- synthetic inputs -------------------------------------------------------
+ * Counter-based generator shared by host oracle and device (splitmix64 of (seed, global index, row)),
+ * PerformanceEval's sampling ranges (PerformanceEval.cpp:59-76): fills a RQCD_BC_ROWS x n matrix at
+ * d_bc (DEVICE pointer) for global indices [index_base, index_base+n). */
+int rqcd_synth_bc(rqcd_ctx* ctx, uint64_t seed, int64_t index_base, int64_t n, double* d_bc, int64_t stride);
+
+/* Measured FP64 issue ceilings of this GPU (for the roofline denominator): runs dependent-free
+ * DFMA and DMUL+DADD loops for about `millis` ms each and returns flop/s, FMA counted as 2. */
+int rqcd_measure_fp64_peak(rqcd_ctx* ctx, int millis, double* dfma_flops, double* dmul_dadd_flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RQCD_H_ */
