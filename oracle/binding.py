@@ -38,22 +38,10 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def make_obstacles(specs) -> "C.Array[abi.Obstacle]":
-    """specs: list of dicts: {type:'sphere', center, radius} | {type:'prism', center, side, quat}
-    optionally with motion (18,), motion_t_start, motion_t_end."""
-    arr = (abi.Obstacle * max(len(specs), 1))()
-    for o, s in zip(arr, specs):
-        o.type = abi.SPHERE if s["type"] == "sphere" else abi.RECT_PRISM
-        o.center[:] = [float(x) for x in s["center"]]
-        o.radius = float(s.get("radius", 0.0))
-        o.side[:] = [float(x) for x in s.get("side", (0.0, 0.0, 0.0))]
-        o.quat[:] = [float(x) for x in s.get("quat", (1.0, 0.0, 0.0, 0.0))]
-        if "motion" in s:
-            o.moving = 1
-            o.motion[:] = [float(x) for x in np.asarray(s["motion"]).reshape(18)]
-            o.motion_t_start = float(s["motion_t_start"])
-            o.motion_t_end = float(s["motion_t_end"])
-    return arr
+def make_obstacles(specs):
+    """See abi.make_obstacles (the struct builder lives with the struct mirrors)."""
+    specs = [dict(s, motion=np.asarray(s["motion"]).reshape(18).tolist()) if "motion" in s else s for s in specs]
+    return abi.make_obstacles(specs)
 
 
 class _CpuImpl:

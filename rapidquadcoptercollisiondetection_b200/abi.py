@@ -120,6 +120,25 @@ SYMBOLS = {
     "rqcd_measure_fp64_peak": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
+def make_obstacles(specs):
+    """Build a ctypes array of rqcd_obstacle from dicts:
+    {type:'sphere', center, radius} | {type:'prism', center, side, quat}, optionally with
+    motion (18,), motion_t_start, motion_t_end for a translating obstacle."""
+    arr = (Obstacle * max(len(specs), 1))()
+    for o, s in zip(arr, specs):
+        o.type = SPHERE if s["type"] == "sphere" else RECT_PRISM
+        o.center[:] = [float(x) for x in s["center"]]
+        o.radius = float(s.get("radius", 0.0))
+        o.side[:] = [float(x) for x in s.get("side", (0.0, 0.0, 0.0))]
+        o.quat[:] = [float(x) for x in s.get("quat", (1.0, 0.0, 0.0, 0.0))]
+        if "motion" in s:
+            o.moving = 1
+            o.motion[:] = [float(x) for x in list(s["motion"])]
+            o.motion_t_start = float(s["motion_t_start"])
+            o.motion_t_end = float(s["motion_t_end"])
+    return arr
+
+
 _lib = None
 
 

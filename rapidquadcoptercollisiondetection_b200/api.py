@@ -1,0 +1,231 @@
+"""Thin Python handle over the C ABI (include/rqcd.h) for tests/ and bench.py.
+
+Every method is one C-ABI call; no arithmetic of the path happens in Python and there is no fallback:
+constructing a Context without librqcd.so or without a CUDA device raises.
+
+Host mode takes/returns numpy arrays (the library stages them); device mode takes raw device pointers
+(ints, e.g. torch.Tensor.data_ptr()) and only enqueues work on the context's stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class RqcdError(RuntimeError):
+    def __init__(self, status: int, text: str, detail: str = ""):
+        super().__init__(f"rqcd status {status}: {text}" + (f" [{detail}]" if detail else ""))
+        self.status = status
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """rqcd_ctx: one GPU, one stream."""
+
+    def __init__(self, device: int = 0):
+        self.lib = abi.load()
+        h = C.c_void_p()
+        st = self.lib.rqcd_create(C.byref(h), device)
+        if st != abi.OK:
+            raise RqcdError(st, self.lib.rqcd_strerror(st).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rqcd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, st, allow=()):
+        if st != abi.OK and st not in allow:
+            raise RqcdError(st, self.lib.rqcd_strerror(st).decode(), self.lib.rqcd_last_error(self.h).decode())
+        return st
+
+    # ---- context ----
+    def device_info(self):
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        name = C.create_string_buffer(256)
+        self._chk(self.lib.rqcd_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), name, 256))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "name": name.value.decode()}
+
+    def set_stream(self, cuda_stream: int | None):
+        self._chk(self.lib.rqcd_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def get_stream(self) -> int:
+        return int(self.lib.rqcd_get_stream(self.h) or 0)
+
+    def synchronize(self):
+        self._chk(self.lib.rqcd_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.rqcd_launch_count(self.h))
+
+    def read_summary(self) -> dict:
+        s = abi.Summary()
+        self._chk(self.lib.rqcd_read_summary(self.h, C.byref(s)), allow=(abi.ERR_DEPTH_CAP,))
+        return s.as_dict()
+
+    def set_obstacles(self, obstacles, m: int | None = None):
+        """obstacles: ctypes array of abi.Obstacle (see oracle.binding.make_obstacles / abi.make_obstacles)."""
+        if m is None:
+            m = len(obstacles)
+        self._chk(self.lib.rqcd_set_obstacles(self.h, obstacles, m))
+        self.m = m
+
+    def num_obstacles(self) -> int:
+        return int(self.lib.rqcd_num_obstacles(self.h))
+
+    # ---- host-mode calls (numpy in / numpy out) ----
+    def generate(self, bc, goal_mask=abi.GOAL_ALL):
+        bc = np.ascontiguousarray(bc, dtype=np.float64)
+        n = bc.shape[1]
+        cost = np.empty(n)
+        coeffs = np.empty((abi.COEFF_ROWS, n))
+        out = abi.Out(cost=_ptr(cost), coeffs=_ptr(coeffs), coeff_stride=n)
+        inp = abi.BcSoa(_ptr(bc), n, goal_mask, 0)
+        self._chk(self.lib.rqcd_generate(self.h, C.byref(inp), n, 0, C.byref(out)))
+        return {"cost": cost, "coeffs": coeffs}
+
+    def _host_out(self, n, m, matrix, coeffs, first=True):
+        res = {"verdict": np.full(n, 255, dtype=np.uint8)}
+        if first:
+            res["first_obstacle"] = np.full(n, -2, dtype=np.int32)
+        if coeffs:
+            res["cost"] = np.empty(n)
+            res["coeffs"] = np.empty((abi.COEFF_ROWS, n))
+        if matrix:
+            res["verdict_matrix"] = np.full((n, max(m, 1)), 255, dtype=np.uint8)
+        summ = abi.Summary()
+        out = abi.Out(verdict=_ptr(res["verdict"]), first_obstacle=_ptr(res.get("first_obstacle")),
+                      verdict_matrix=_ptr(res.get("verdict_matrix")), cost=_ptr(res.get("cost")),
+                      coeffs=_ptr(res.get("coeffs")), coeff_stride=n, summary=C.pointer(summ))
+        return res, out, summ
+
+    def generate_check(self, bc, min_t, goal_mask=abi.GOAL_ALL, flags=0, index_base=0, matrix=True):
+        bc = np.ascontiguousarray(bc, dtype=np.float64)
+        n = bc.shape[1]
+        m = self.num_obstacles()
+        res, out, summ = self._host_out(n, m, matrix and not (flags & abi.F_EARLY_EXIT), True)
+        inp = abi.BcSoa(_ptr(bc), n, goal_mask, 0)
+        st = self._chk(self.lib.rqcd_generate_check(self.h, C.byref(inp), n, min_t, flags, index_base, C.byref(out)),
+                       allow=(abi.ERR_DEPTH_CAP,))
+        res["summary"] = summ.as_dict()
+        res["status"] = st
+        return res
+
+    def check(self, coeffs, t_end, min_t, t_start=None, cost=None, flags=0, index_base=0, matrix=True):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        n = coeffs.shape[1]
+        m = self.num_obstacles()
+        t_end = np.ascontiguousarray(t_end, dtype=np.float64)
+        if t_start is not None:
+            t_start = np.ascontiguousarray(t_start, dtype=np.float64)
+        if cost is not None:
+            cost = np.ascontiguousarray(cost, dtype=np.float64)
+        res, out, summ = self._host_out(n, m, matrix and not (flags & abi.F_EARLY_EXIT), False)
+        inp = abi.CoeffSoa(_ptr(coeffs), n, _ptr(t_start), _ptr(t_end))
+        st = self._chk(self.lib.rqcd_check(self.h, C.byref(inp), _ptr(cost), n, min_t, flags, index_base, C.byref(out)),
+                       allow=(abi.ERR_DEPTH_CAP,))
+        res["summary"] = summ.as_dict()
+        res["status"] = st
+        return res
+
+    def generate_check_pairwise(self, bc, spheres, min_t, goal_mask=abi.GOAL_ALL, index_base=0):
+        bc = np.ascontiguousarray(bc, dtype=np.float64)
+        spheres = np.ascontiguousarray(spheres, dtype=np.float64)
+        n = bc.shape[1]
+        res, out, summ = self._host_out(n, 1, False, True, first=False)
+        inp = abi.BcSoa(_ptr(bc), n, goal_mask, 0)
+        st = self._chk(self.lib.rqcd_generate_check_pairwise(self.h, C.byref(inp), _ptr(spheres), n, n, min_t, 0,
+                                                             index_base, C.byref(out)), allow=(abi.ERR_DEPTH_CAP,))
+        res["summary"] = summ.as_dict()
+        res["status"] = st
+        return res
+
+    def solve_cubic(self, coef):
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        n = coef.shape[1]
+        roots = np.full((3, n), np.nan)
+        cnt = np.zeros(n, dtype=np.int32)
+        self._chk(self.lib.rqcd_solve_cubic(self.h, _ptr(coef), n, 0, _ptr(roots), _ptr(cnt)))
+        return roots, cnt
+
+    def solve_quartic(self, coef):
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        n = coef.shape[1]
+        roots = np.full((4, n), np.nan)
+        cnt = np.zeros(n, dtype=np.int32)
+        self._chk(self.lib.rqcd_solve_quartic(self.h, _ptr(coef), n, 0, _ptr(roots), _ptr(cnt)))
+        return roots, cnt
+
+    # ---- device-mode calls (raw device pointers; asynchronous on the context's stream) ----
+    def synth_bc(self, seed, index_base, n, d_bc: int, stride: int):
+        self._chk(self.lib.rqcd_synth_bc(self.h, seed, index_base, n, C.c_void_p(d_bc), stride))
+
+    def generate_check_dev(self, d_bc: int, stride: int, n: int, min_t: float, goal_mask=abi.GOAL_ALL, flags=0,
+                           index_base=0, d_verdict=0, d_first=0, d_matrix=0, d_cost=0, d_coeffs=0, coeff_stride=0,
+                           want_summary=False):
+        summ = abi.Summary()
+        out = abi.Out(verdict=d_verdict or None, first_obstacle=d_first or None, verdict_matrix=d_matrix or None,
+                      cost=d_cost or None, coeffs=d_coeffs or None, coeff_stride=coeff_stride,
+                      summary=C.pointer(summ) if want_summary else None)
+        inp = abi.BcSoa(C.c_void_p(d_bc), stride, goal_mask, 0)
+        st = self._chk(self.lib.rqcd_generate_check(self.h, C.byref(inp), n, min_t, flags | abi.F_DEVICE_PTRS,
+                                                    index_base, C.byref(out)), allow=(abi.ERR_DEPTH_CAP,))
+        return summ.as_dict() if want_summary else st
+
+    def generate_check_pairwise_dev(self, d_bc: int, stride: int, d_spheres: int, sphere_stride: int, n: int,
+                                    min_t: float, goal_mask=abi.GOAL_ALL, index_base=0, d_verdict=0, d_cost=0,
+                                    want_summary=False):
+        summ = abi.Summary()
+        out = abi.Out(verdict=d_verdict or None, cost=d_cost or None,
+                      summary=C.pointer(summ) if want_summary else None)
+        inp = abi.BcSoa(C.c_void_p(d_bc), stride, goal_mask, 0)
+        st = self._chk(self.lib.rqcd_generate_check_pairwise(self.h, C.byref(inp), C.c_void_p(d_spheres), sphere_stride,
+                                                             n, min_t, abi.F_DEVICE_PTRS, index_base, C.byref(out)),
+                       allow=(abi.ERR_DEPTH_CAP,))
+        return summ.as_dict() if want_summary else st
+
+    def measure_fp64_peak(self, millis=200):
+        a, b = C.c_double(), C.c_double()
+        self._chk(self.lib.rqcd_measure_fp64_peak(self.h, millis, C.byref(a), C.byref(b)))
+        return {"dfma_flops": a.value, "dmul_dadd_flops": b.value}
+
+
+def merge_summaries(summaries) -> dict:
+    """rqcd_merge_summaries over a list of summary dicts (the multi-GPU exchange step)."""
+    lib = abi.load()
+    arr = (abi.Summary * max(len(summaries), 1))()
+    for dst, s in zip(arr, summaries):
+        dst.traj_counts[:] = s["traj_counts"]
+        dst.pair_counts[:] = s["pair_counts"]
+        dst.pairs_checked = s["pairs_checked"]
+        dst.best_cost = s["best_cost"]
+        dst.best_index = s["best_index"]
+    out = abi.Summary()
+    st = lib.rqcd_merge_summaries(arr, len(summaries), C.byref(out))
+    if st != abi.OK:
+        raise RqcdError(st, lib.rqcd_strerror(st).decode())
+    return out.as_dict()

@@ -1,0 +1,691 @@
+// rqcd_api.cu -- the C ABI of include/rqcd.h: context, obstacle upload, staging for host buffers and the
+// launches. Host logic only; all arithmetic of the path lives in rqcd_kernels.cu / rqcd_device.cuh, except
+// the per-obstacle constants hoisted in prepare_obstacle() below.
+//
+// There is no CPU implementation of the path in this library: without a CUDA device rqcd_create fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <vector>
+
+#include "../../include/rqcd.h"
+#include "rqcd_device.cuh"
+#include "rqcd_kernels.cuh"
+
+using namespace rqcd;
+
+static_assert(RQCD_MAX_DEPTH == kMaxDepth, "RQCD_MAX_DEPTH and the device stack size must agree");
+static_assert(sizeof(DevSummary) == sizeof(rqcd_summary), "DevSummary mirrors rqcd_summary");
+
+namespace {
+
+constexpr size_t kMaxSmem = 227 * 1024;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct rqcd_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaDeviceProp prop;
+  // obstacle set
+  int m = 0, mp = 0, nfields = OF_STATIC_FIELDS;
+  bool any_moving = false;
+  DevBuf obs_blob;
+  // launch scratch
+  unsigned long long* d_counter = nullptr;
+  BlockPartial* d_partials = nullptr;
+  int partial_cap = 0;
+  DevSummary* d_summary = nullptr;
+  DevSummary* h_summary = nullptr;  // pinned
+  bool summary_valid = false;
+  // staging for host-pointer calls
+  DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count;
+  int refill_min = 4;
+  unsigned long long launches = 0;
+  char last_error[512] = {0};
+};
+
+namespace {
+
+int fail_cuda(rqcd_ctx* c, cudaError_t e, const char* what) {
+  snprintf(c->last_error, sizeof c->last_error, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return RQCD_ERR_CUDA;
+}
+
+#define RQCD_CU(call)                                        \
+  do {                                                       \
+    cudaError_t e_ = (call);                                 \
+    if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call); \
+  } while (0)
+
+struct DeviceGuard {  // the context's device is current for the duration of a call
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+cudaError_t ensure(DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return cudaSuccess;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) return e;
+  b.cap = want;
+  return cudaSuccess;
+}
+
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+bool finite3(const double* v) { return std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]); }
+
+// Rotation::GetRotationMatrix (include/CommonMath/Rotation.hpp:203-220), same expression order, so that
+// hoisting it out of Rotation::Rotate (Rotation.hpp:224-233) is bit-identical to rebuilding it per call.
+void rotation_matrix(const double v[4], double R[9]) {
+  const double r0 = v[0] * v[0];
+  const double r1 = v[1] * v[1];
+  const double r2 = v[2] * v[2];
+  const double r3 = v[3] * v[3];
+  R[0] = r0 + r1 - r2 - r3;
+  R[1] = 2 * v[1] * v[2] - 2 * v[0] * v[3];
+  R[2] = 2 * v[1] * v[3] + 2 * v[0] * v[2];
+  R[3] = 2 * v[1] * v[2] + 2 * v[0] * v[3];
+  R[4] = r0 - r1 + r2 - r3;
+  R[5] = 2 * v[2] * v[3] - 2 * v[0] * v[1];
+  R[6] = 2 * v[1] * v[3] - 2 * v[0] * v[2];
+  R[7] = 2 * v[2] * v[3] + 2 * v[0] * v[1];
+  R[8] = r0 - r1 - r2 + r3;
+}
+
+int validate_obstacle(const rqcd_obstacle& o) {
+  if (o.type != RQCD_SPHERE && o.type != RQCD_RECT_PRISM) return RQCD_ERR_UNSUPPORTED;
+  if (o.moving != 0 && o.moving != 1) return RQCD_ERR_INVALID_ARG;
+  if (!finite3(o.center)) return RQCD_ERR_INVALID_ARG;
+  if (o.type == RQCD_SPHERE) {
+    if (!(o.radius > 0) || !std::isfinite(o.radius)) return RQCD_ERR_INVALID_ARG;  // Sphere.hpp:44
+  } else {
+    if (!(o.side[0] > 0 && o.side[1] > 0 && o.side[2] > 0) || !finite3(o.side)) return RQCD_ERR_INVALID_ARG;  // RectPrism.hpp:52
+    for (int i = 0; i < 4; i++)
+      if (!std::isfinite(o.quat[i])) return RQCD_ERR_INVALID_ARG;
+  }
+  if (o.moving) {
+    for (int i = 0; i < 18; i++)
+      if (!std::isfinite(o.motion[i])) return RQCD_ERR_INVALID_ARG;
+    if (!(o.motion_t_start <= o.motion_t_end)) return RQCD_ERR_INVALID_ARG;  // Trajectory.hpp:68
+  }
+  return RQCD_OK;
+}
+
+int ensure_partials(rqcd_ctx* ctx, int grid) {
+  if (grid <= ctx->partial_cap) return RQCD_OK;
+  if (ctx->d_partials) cudaFree(ctx->d_partials);
+  ctx->d_partials = nullptr;
+  ctx->partial_cap = 0;
+  RQCD_CU(cudaMalloc(&ctx->d_partials, sizeof(BlockPartial) * (size_t)grid));
+  ctx->partial_cap = grid;
+  return RQCD_OK;
+}
+
+// Everything below `what the caller passed` is device memory here.
+struct CheckCall {
+  int mode = MODE_BC;
+  bool pairwise = false;
+  CheckParams p = {};
+};
+
+int run_check(rqcd_ctx* ctx, CheckCall& cc) {
+  const bool moving = !cc.pairwise && ctx->any_moving;
+  CheckParams& p = cc.p;
+  p.obs_blob = ctx->obs_blob.p;
+  p.m = cc.pairwise ? 1 : ctx->m;
+  p.mp = ctx->mp;
+  p.nfields = ctx->nfields;
+  p.refill_min = ctx->refill_min;
+  p.work_counter = ctx->d_counter;
+  const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->nfields, moving);
+  if (smem > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
+  RQCD_CU(check_prepare(cc.mode, moving, cc.pairwise, smem));
+  int per_sm = check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, smem);
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)ctx->prop.multiProcessorCount * per_sm;
+  const long long need = (p.n + kThreads - 1) / kThreads;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  int st = ensure_partials(ctx, (int)grid);
+  if (st != RQCD_OK) return st;
+  p.partials = ctx->d_partials;
+  RQCD_CU(launch_check(p, cc.mode, moving, cc.pairwise, (int)grid, ctx->stream, ctx->d_summary));
+  ctx->launches += 2;  // k_check + k_finalize
+  ctx->summary_valid = true;
+  return RQCD_OK;
+}
+
+int fetch_summary(rqcd_ctx* ctx, rqcd_summary* out) {
+  RQCD_CU(cudaMemcpyAsync(ctx->h_summary, ctx->d_summary, sizeof(DevSummary), cudaMemcpyDeviceToHost, ctx->stream));
+  RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->h_summary, sizeof(rqcd_summary));
+  if (out->traj_counts[3] != 0 || out->pair_counts[3] != 0) return RQCD_ERR_DEPTH_CAP;
+  return RQCD_OK;
+}
+
+bool bad_min_t(double t) { return !(t > 0) || !std::isfinite(t); }
+
+// Host <-> device staging of row matrices (row r at base + r*stride, n doubles each).
+cudaError_t rows_h2d(void* dst, const double* src, long long stride, long long n, int rows, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  return cudaMemcpy2DAsync(dst, (size_t)n * 8, src, (size_t)stride * 8, (size_t)n * 8, rows, cudaMemcpyHostToDevice, s);
+}
+cudaError_t rows_d2h(double* dst, long long stride, const void* src, long long n, int rows, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  return cudaMemcpy2DAsync(dst, (size_t)stride * 8, src, (size_t)n * 8, (size_t)n * 8, rows, cudaMemcpyDeviceToHost, s);
+}
+
+struct OutStage {  // device-side output pointers + what must be copied back
+  uint8_t* verdict = nullptr;
+  int* first = nullptr;
+  uint8_t* matrix = nullptr;
+  double* cost = nullptr;
+  double* coeffs = nullptr;
+  long long coeff_stride = 0;
+};
+
+int stage_outputs(rqcd_ctx* ctx, const rqcd_out* out, long long n, int m, bool want_cost_coeffs, OutStage& o) {
+  if (out->verdict) {
+    RQCD_CU(ensure(ctx->s_verdict, (size_t)n));
+    o.verdict = (uint8_t*)ctx->s_verdict.p;
+  }
+  if (out->first_obstacle) {
+    RQCD_CU(ensure(ctx->s_first, (size_t)n * 4));
+    o.first = (int*)ctx->s_first.p;
+  }
+  if (out->verdict_matrix) {
+    RQCD_CU(ensure(ctx->s_matrix, (size_t)n * (size_t)(m > 0 ? m : 1)));
+    o.matrix = (uint8_t*)ctx->s_matrix.p;
+  }
+  if (want_cost_coeffs && out->cost) {
+    RQCD_CU(ensure(ctx->s_cost, (size_t)n * 8));
+    o.cost = (double*)ctx->s_cost.p;
+  }
+  if (want_cost_coeffs && out->coeffs) {
+    RQCD_CU(ensure(ctx->s_coeffs, (size_t)n * 8 * RQCD_COEFF_ROWS));
+    o.coeffs = (double*)ctx->s_coeffs.p;
+    o.coeff_stride = n;
+  }
+  return RQCD_OK;
+}
+
+int copy_back(rqcd_ctx* ctx, const rqcd_out* out, long long n, int m, const OutStage& o) {
+  cudaStream_t s = ctx->stream;
+  if (n == 0) return RQCD_OK;
+  if (o.verdict) RQCD_CU(cudaMemcpyAsync(out->verdict, o.verdict, (size_t)n, cudaMemcpyDeviceToHost, s));
+  if (o.first) RQCD_CU(cudaMemcpyAsync(out->first_obstacle, o.first, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  if (o.matrix && m > 0)
+    RQCD_CU(cudaMemcpyAsync(out->verdict_matrix, o.matrix, (size_t)n * (size_t)m, cudaMemcpyDeviceToHost, s));
+  if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost, o.cost, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  if (o.coeffs) RQCD_CU(rows_d2h(out->coeffs, out->coeff_stride, o.coeffs, n, RQCD_COEFF_ROWS, s));
+  return RQCD_OK;
+}
+
+void fill_params_out(CheckParams& p, const OutStage& o) {
+  p.verdict = o.verdict;
+  p.first_obstacle = o.first;
+  p.verdict_matrix = o.matrix;
+  p.cost = o.cost;
+  p.coeffs = o.coeffs;
+  p.coeff_stride = o.coeff_stride;
+}
+
+int validate_out(const rqcd_out* out, uint32_t flags, long long n) {
+  if (!out) return RQCD_ERR_INVALID_ARG;
+  if ((flags & RQCD_F_EARLY_EXIT) && out->verdict_matrix) return RQCD_ERR_INVALID_ARG;
+  if (out->coeffs && out->coeff_stride < n) return RQCD_ERR_INVALID_ARG;
+  return RQCD_OK;
+}
+
+// Shared tail of the three check entry points once the inputs are on the device.
+int finish_check(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, uint32_t flags, long long n, int m,
+                 bool want_cost_coeffs) {
+  OutStage o;
+  const bool dev = flags & RQCD_F_DEVICE_PTRS;
+  if (dev) {
+    o.verdict = out->verdict;
+    o.first = out->first_obstacle;
+    o.matrix = out->verdict_matrix;
+    if (want_cost_coeffs) {
+      o.cost = out->cost;
+      o.coeffs = out->coeffs;
+      o.coeff_stride = out->coeff_stride;
+    }
+  } else {
+    int st = stage_outputs(ctx, out, n, m, want_cost_coeffs, o);
+    if (st != RQCD_OK) return st;
+  }
+  fill_params_out(cc.p, o);
+  cc.p.early_exit = (flags & RQCD_F_EARLY_EXIT) ? 1 : 0;
+  int st = run_check(ctx, cc);
+  if (st != RQCD_OK) return st;
+  if (!dev) {
+    st = copy_back(ctx, out, n, m, o);
+    if (st != RQCD_OK) return st;
+  }
+  if (out->summary) return fetch_summary(ctx, out->summary);
+  if (!dev) RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  return RQCD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rqcd_create(rqcd_ctx** out, int device) {
+  if (!out) return RQCD_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return RQCD_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) return RQCD_ERR_INVALID_ARG;
+  rqcd_ctx* ctx = new (std::nothrow) rqcd_ctx();
+  if (!ctx) return RQCD_ERR_NOMEM;
+  ctx->device = device;
+  if (cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess || ctx->prop.major < 10) {
+    cudaGetLastError();
+    delete ctx;
+    return RQCD_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
+  }
+  DeviceGuard g(device);
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counter, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_summary, sizeof(DevSummary));
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_summary, sizeof(DevSummary));
+  if (e != cudaSuccess) {
+    rqcd_destroy(ctx);
+    return RQCD_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  const char* rm = getenv("RQCD_REFILL_MIN");
+  if (rm && atoi(rm) >= 1 && atoi(rm) <= 32) ctx->refill_min = atoi(rm);
+  *out = ctx;
+  return RQCD_OK;
+}
+
+void rqcd_destroy(rqcd_ctx* ctx) {
+  if (!ctx) return;
+  DeviceGuard g(ctx->device);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  release(ctx->obs_blob);
+  DevBuf* bufs[] = {&ctx->s_in,   &ctx->s_aux,    &ctx->s_verdict, &ctx->s_first, &ctx->s_matrix,
+                    &ctx->s_cost, &ctx->s_coeffs, &ctx->s_roots,   &ctx->s_count};
+  for (DevBuf* b : bufs) release(*b);
+  if (ctx->d_counter) cudaFree(ctx->d_counter);
+  if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_summary) cudaFree(ctx->d_summary);
+  if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* rqcd_strerror(int status) {
+  switch (status) {
+    case RQCD_OK: return "ok";
+    case RQCD_ERR_INVALID_ARG: return "invalid argument";
+    case RQCD_ERR_CUDA: return "CUDA runtime error (see rqcd_last_error)";
+    case RQCD_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (this library has no CPU fallback)";
+    case RQCD_ERR_DEPTH_CAP: return "interval-stack cap hit: (t_end - t_start)/min_time_section is too large";
+    case RQCD_ERR_NOMEM: return "out of memory";
+    case RQCD_ERR_UNSUPPORTED: return "unsupported obstacle type or obstacle set too large for shared memory";
+    default: return "unknown status";
+  }
+}
+
+const char* rqcd_last_error(const rqcd_ctx* ctx) { return ctx ? ctx->last_error : ""; }
+
+int rqcd_device_info(const rqcd_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, char* name, size_t name_len) {
+  if (!ctx) return RQCD_ERR_INVALID_ARG;
+  if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+  if (cc_major) *cc_major = ctx->prop.major;
+  if (cc_minor) *cc_minor = ctx->prop.minor;
+  if (name && name_len > 0) {
+    strncpy(name, ctx->prop.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  return RQCD_OK;
+}
+
+void* rqcd_get_stream(const rqcd_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int rqcd_set_stream(rqcd_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return RQCD_ERR_INVALID_ARG;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return RQCD_OK;
+}
+
+int rqcd_synchronize(rqcd_ctx* ctx) {
+  if (!ctx) return RQCD_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  return RQCD_OK;
+}
+
+int rqcd_read_summary(rqcd_ctx* ctx, rqcd_summary* out) {
+  if (!ctx || !out || !ctx->summary_valid) return RQCD_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  return fetch_summary(ctx, out);
+}
+
+uint64_t rqcd_launch_count(const rqcd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rqcd_set_obstacles(rqcd_ctx* ctx, const rqcd_obstacle* obstacles, int32_t m) {
+  if (!ctx || m < 0 || (m > 0 && !obstacles)) return RQCD_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  bool any_moving = false;
+  for (int k = 0; k < m; k++) {
+    int st = validate_obstacle(obstacles[k]);
+    if (st != RQCD_OK) return st;
+    any_moving = any_moving || obstacles[k].moving;
+  }
+  const int nfields = any_moving ? OF_MOVING_FIELDS : OF_STATIC_FIELDS;
+  const int mp = (m + 3) / 4 * 4;
+  if (check_smem_bytes(mp, nfields, any_moving) > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
+  const size_t bytes = (size_t)nfields * mp * 8 + (size_t)mp * 4;
+  std::vector<unsigned char> blob(bytes > 0 ? bytes : 16, 0);
+  double* tab = reinterpret_cast<double*>(blob.data());
+  int* fl = reinterpret_cast<int*>(blob.data() + (size_t)nfields * mp * 8);
+  for (int k = 0; k < m; k++) {
+    const rqcd_obstacle& o = obstacles[k];
+    auto F = [&](int f) -> double& { return tab[(size_t)f * mp + k]; };
+    F(OF_CX) = o.center[0];
+    F(OF_CY) = o.center[1];
+    F(OF_CZ) = o.center[2];
+    int flags = 0;
+    if (o.type == RQCD_SPHERE) {
+      F(OF_H0) = o.radius;
+    } else {
+      flags |= OBS_PRISM;
+      for (int i = 0; i < 3; i++) F(OF_H0 + i) = o.side[i] / 2;  // RectPrism.hpp:72-75, :97-99
+      double R[9], Ri[9];
+      const double qi[4] = {o.quat[0], -o.quat[1], -o.quat[2], -o.quat[3]};  // Rotation::Inverse, Rotation.hpp:63-65
+      rotation_matrix(o.quat, R);
+      rotation_matrix(qi, Ri);
+      for (int i = 0; i < 9; i++) {
+        F(OF_R + i) = R[i];
+        F(OF_RI + i) = Ri[i];
+      }
+    }
+    if (o.moving) {
+      flags |= OBS_MOVING;
+      for (int i = 0; i < 18; i++) F(OF_MOTION + i) = o.motion[i];
+      F(OF_MT0) = o.motion_t_start;
+      F(OF_MT1) = o.motion_t_end;
+    }
+    fl[k] = flags;
+  }
+  RQCD_CU(ensure(ctx->obs_blob, blob.size()));
+  // synchronous on purpose: the blob is a stack-lifetime host vector, and a previous launch may still read the old set
+  RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  RQCD_CU(cudaMemcpy(ctx->obs_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  ctx->m = m;
+  ctx->mp = mp;
+  ctx->nfields = nfields;
+  ctx->any_moving = any_moving;
+  return RQCD_OK;
+}
+
+int32_t rqcd_num_obstacles(const rqcd_ctx* ctx) { return ctx ? ctx->m : -1; }
+
+int rqcd_generate(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, uint32_t flags, rqcd_out* out) {
+  if (!ctx || !in || !out || n < 0 || (n > 0 && !in->data) || in->stride < n) return RQCD_ERR_INVALID_ARG;
+  if (out->coeffs && out->coeff_stride < n) return RQCD_ERR_INVALID_ARG;
+  if (n == 0) return RQCD_OK;
+  DeviceGuard g(ctx->device);
+  if (flags & RQCD_F_DEVICE_PTRS) {
+    RQCD_CU(launch_generate(in->data, in->stride, in->goal_mask, n, out->cost, out->coeffs, out->coeff_stride, ctx->stream));
+    ctx->launches++;
+    return RQCD_OK;
+  }
+  RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
+  RQCD_CU(rows_h2d(ctx->s_in.p, in->data, in->stride, n, RQCD_BC_ROWS, ctx->stream));
+  OutStage o;
+  if (out->cost) {
+    RQCD_CU(ensure(ctx->s_cost, (size_t)n * 8));
+    o.cost = (double*)ctx->s_cost.p;
+  }
+  if (out->coeffs) {
+    RQCD_CU(ensure(ctx->s_coeffs, (size_t)n * 8 * RQCD_COEFF_ROWS));
+    o.coeffs = (double*)ctx->s_coeffs.p;
+    o.coeff_stride = n;
+  }
+  RQCD_CU(launch_generate((const double*)ctx->s_in.p, n, in->goal_mask, n, o.cost, o.coeffs, o.coeff_stride, ctx->stream));
+  ctx->launches++;
+  if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost, o.cost, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (o.coeffs) RQCD_CU(rows_d2h(out->coeffs, out->coeff_stride, o.coeffs, n, RQCD_COEFF_ROWS, ctx->stream));
+  RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  return RQCD_OK;
+}
+
+int rqcd_generate_check(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, double min_time_section, uint32_t flags,
+                        int64_t index_base, rqcd_out* out) {
+  if (!ctx || !in || n < 0 || (n > 0 && !in->data) || in->stride < n || bad_min_t(min_time_section))
+    return RQCD_ERR_INVALID_ARG;
+  int st = validate_out(out, flags, n);
+  if (st != RQCD_OK) return st;
+  DeviceGuard g(ctx->device);
+  CheckCall cc;
+  cc.mode = MODE_BC;
+  cc.p.goal_mask = in->goal_mask;
+  cc.p.n = n;
+  cc.p.index_base = index_base;
+  cc.p.min_t = min_time_section;
+  if (flags & RQCD_F_DEVICE_PTRS) {
+    cc.p.in = in->data;
+    cc.p.in_stride = in->stride;
+  } else {
+    RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
+    RQCD_CU(rows_h2d(ctx->s_in.p, in->data, in->stride, n, RQCD_BC_ROWS, ctx->stream));
+    cc.p.in = (const double*)ctx->s_in.p;
+    cc.p.in_stride = n;
+  }
+  return finish_check(ctx, cc, out, flags, n, ctx->m, true);
+}
+
+int rqcd_check(rqcd_ctx* ctx, const rqcd_coeff_soa* in, const double* cost, int64_t n, double min_time_section,
+               uint32_t flags, int64_t index_base, rqcd_out* out) {
+  if (!ctx || !in || n < 0 || (n > 0 && (!in->coeffs || !in->t_end)) || in->stride < n || bad_min_t(min_time_section))
+    return RQCD_ERR_INVALID_ARG;
+  int st = validate_out(out, flags, n);
+  if (st != RQCD_OK) return st;
+  DeviceGuard g(ctx->device);
+  CheckCall cc;
+  cc.mode = MODE_COEFF;
+  cc.p.n = n;
+  cc.p.index_base = index_base;
+  cc.p.min_t = min_time_section;
+  if (flags & RQCD_F_DEVICE_PTRS) {
+    cc.p.in = in->coeffs;
+    cc.p.in_stride = in->stride;
+    cc.p.t_start = in->t_start;
+    cc.p.t_end = in->t_end;
+    cc.p.cost_in = cost;
+  } else {
+    RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_COEFF_ROWS));
+    RQCD_CU(ensure(ctx->s_aux, (size_t)n * 8 * 3));
+    double* aux = (double*)ctx->s_aux.p;
+    RQCD_CU(rows_h2d(ctx->s_in.p, in->coeffs, in->stride, n, RQCD_COEFF_ROWS, ctx->stream));
+    if (n > 0) {
+      RQCD_CU(cudaMemcpyAsync(aux, in->t_end, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+      if (in->t_start) RQCD_CU(cudaMemcpyAsync(aux + n, in->t_start, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+      if (cost) RQCD_CU(cudaMemcpyAsync(aux + 2 * n, cost, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    cc.p.in = (const double*)ctx->s_in.p;
+    cc.p.in_stride = n;
+    cc.p.t_end = aux;
+    cc.p.t_start = in->t_start ? aux + n : nullptr;
+    cc.p.cost_in = cost ? aux + 2 * n : nullptr;
+  }
+  // Trajectory's constructor asserts startTime <= endTime (Trajectory.hpp:68); windows that violate it are
+  // checked like any other input here (the section loop simply sees tf - ts < minT).
+  return finish_check(ctx, cc, out, flags, n, ctx->m, false);
+}
+
+int rqcd_generate_check_pairwise(rqcd_ctx* ctx, const rqcd_bc_soa* in, const double* spheres, int64_t sphere_stride,
+                                 int64_t n, double min_time_section, uint32_t flags, int64_t index_base, rqcd_out* out) {
+  if (!ctx || !in || n < 0 || (n > 0 && (!in->data || !spheres)) || in->stride < n || sphere_stride < n ||
+      bad_min_t(min_time_section))
+    return RQCD_ERR_INVALID_ARG;
+  int st = validate_out(out, flags, n);
+  if (st != RQCD_OK) return st;
+  if (out->verdict_matrix || out->first_obstacle) return RQCD_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  CheckCall cc;
+  cc.mode = MODE_BC;
+  cc.pairwise = true;
+  cc.p.goal_mask = in->goal_mask;
+  cc.p.n = n;
+  cc.p.index_base = index_base;
+  cc.p.min_t = min_time_section;
+  if (flags & RQCD_F_DEVICE_PTRS) {
+    cc.p.in = in->data;
+    cc.p.in_stride = in->stride;
+    cc.p.spheres = spheres;
+    cc.p.sphere_stride = sphere_stride;
+  } else {
+    RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
+    RQCD_CU(ensure(ctx->s_aux, (size_t)n * 8 * 4));
+    RQCD_CU(rows_h2d(ctx->s_in.p, in->data, in->stride, n, RQCD_BC_ROWS, ctx->stream));
+    RQCD_CU(rows_h2d(ctx->s_aux.p, spheres, sphere_stride, n, 4, ctx->stream));
+    cc.p.in = (const double*)ctx->s_in.p;
+    cc.p.in_stride = n;
+    cc.p.spheres = (const double*)ctx->s_aux.p;
+    cc.p.sphere_stride = n;
+  }
+  return finish_check(ctx, cc, out, flags & ~RQCD_F_EARLY_EXIT, n, 1, true);
+}
+
+static int solve_common(rqcd_ctx* ctx, bool quartic, const double* coef, int64_t n, uint32_t flags, double* roots,
+                        int32_t* count) {
+  if (!ctx || n < 0 || (n > 0 && (!coef || !roots || !count))) return RQCD_ERR_INVALID_ARG;
+  if (n == 0) return RQCD_OK;
+  DeviceGuard g(ctx->device);
+  const int rows = quartic ? 4 : 3;
+  if (flags & RQCD_F_DEVICE_PTRS) {
+    RQCD_CU(launch_solve(quartic, coef, n, roots, count, ctx->stream));
+    ctx->launches++;
+    return RQCD_OK;
+  }
+  RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * rows));
+  RQCD_CU(ensure(ctx->s_roots, (size_t)n * 8 * rows));
+  RQCD_CU(ensure(ctx->s_count, (size_t)n * 4));
+  RQCD_CU(cudaMemcpyAsync(ctx->s_in.p, coef, (size_t)n * 8 * rows, cudaMemcpyHostToDevice, ctx->stream));
+  RQCD_CU(launch_solve(quartic, (const double*)ctx->s_in.p, n, (double*)ctx->s_roots.p, (int*)ctx->s_count.p, ctx->stream));
+  ctx->launches++;
+  RQCD_CU(cudaMemcpyAsync(roots, ctx->s_roots.p, (size_t)n * 8 * rows, cudaMemcpyDeviceToHost, ctx->stream));
+  RQCD_CU(cudaMemcpyAsync(count, ctx->s_count.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  return RQCD_OK;
+}
+
+int rqcd_solve_cubic(rqcd_ctx* ctx, const double* coef, int64_t n, uint32_t flags, double* roots, int32_t* count) {
+  return solve_common(ctx, false, coef, n, flags, roots, count);
+}
+int rqcd_solve_quartic(rqcd_ctx* ctx, const double* coef, int64_t n, uint32_t flags, double* roots, int32_t* count) {
+  return solve_common(ctx, true, coef, n, flags, roots, count);
+}
+
+int rqcd_merge_summaries(const rqcd_summary* shards, int32_t n_shards, rqcd_summary* merged) {
+  if (!merged || n_shards < 0 || (n_shards > 0 && !shards)) return RQCD_ERR_INVALID_ARG;
+  memset(merged, 0, sizeof *merged);
+  merged->best_cost = std::numeric_limits<double>::infinity();
+  merged->best_index = -1;
+  for (int k = 0; k < n_shards; k++) {
+    const rqcd_summary& s = shards[k];
+    for (int v = 0; v < 4; v++) {
+      merged->traj_counts[v] += s.traj_counts[v];
+      merged->pair_counts[v] += s.pair_counts[v];
+    }
+    merged->pairs_checked += s.pairs_checked;
+    if (s.best_index >= 0 && (merged->best_index < 0 || s.best_cost < merged->best_cost ||
+                              (s.best_cost == merged->best_cost && s.best_index < merged->best_index))) {
+      merged->best_cost = s.best_cost;
+      merged->best_index = s.best_index;
+    }
+  }
+  return RQCD_OK;
+}
+
+int rqcd_synth_bc(rqcd_ctx* ctx, uint64_t seed, int64_t index_base, int64_t n, double* d_bc, int64_t stride) {
+  if (!ctx || n < 0 || (n > 0 && !d_bc) || stride < n) return RQCD_ERR_INVALID_ARG;
+  if (n == 0) return RQCD_OK;
+  DeviceGuard g(ctx->device);
+  RQCD_CU(launch_synth_bc(seed, index_base, n, d_bc, stride, ctx->stream));
+  ctx->launches++;
+  return RQCD_OK;
+}
+
+int rqcd_measure_fp64_peak(rqcd_ctx* ctx, int millis, double* dfma_flops, double* dmul_dadd_flops) {
+  if (!ctx || millis <= 0) return RQCD_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  double* sink = nullptr;
+  RQCD_CU(cudaMalloc(&sink, 8));
+  cudaEvent_t e0, e1;
+  RQCD_CU(cudaEventCreate(&e0));
+  RQCD_CU(cudaEventCreate(&e1));
+  const int blocks = ctx->prop.multiProcessorCount * 8;
+  int status = RQCD_OK;
+  for (int pass = 0; pass < 2 && status == RQCD_OK; pass++) {
+    const bool fma = pass == 0;
+    double* dst = fma ? dfma_flops : dmul_dadd_flops;
+    int iters = 256;
+    float ms = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {  // warm-up, calibration, measurement
+      cudaError_t e = cudaEventRecord(e0, ctx->stream);
+      if (e == cudaSuccess) e = launch_fp64_peak(fma, blocks, iters, sink, ctx->stream);
+      if (e == cudaSuccess) e = cudaEventRecord(e1, ctx->stream);
+      if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+      if (e != cudaSuccess) {
+        status = fail_cuda(ctx, e, "fp64 peak");
+        break;
+      }
+      ctx->launches++;
+      if (attempt == 1 && ms > 0) {
+        double scale = (double)millis / ms;
+        long long it = (long long)(iters * scale);
+        if (it < 64) it = 64;
+        if (it > (1 << 24)) it = 1 << 24;
+        iters = (int)it;
+      }
+    }
+    if (status == RQCD_OK && dst) {
+      const double ops = (double)blocks * kPeakThreads * kPeakChains * kPeakInnerOps * (double)iters;
+      *dst = ops * (fma ? 2.0 : 1.0) / (ms * 1e-3);
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return status;
+}
+
+}  // extern "C"

@@ -1,0 +1,545 @@
+// rqcd_kernels.cu -- CUDA kernels of the hot path for sm_100a. Compile with -fmad=false (see rqcd_device.cuh).
+//
+// k_check is the fused kernel: RapidTrajectoryGenerator::Generate -> GetTrajectory ->
+// CollisionChecker::CollisionCheck against the whole obstacle set, i.e. the candidate-loop body of
+// test/ForestPerformanceEval.cpp:186-225 (and, in pairwise form, test/PerformanceEval.cpp:140-182).
+//
+// Shape of the kernel
+//   * persistent CTAs (grid = SMs x resident CTAs); the prepared obstacle table is staged once per CTA into
+//     shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) and reused by every candidate.
+//   * a lane owns one trajectory (its 18 coefficients live in registers) and walks the obstacles on its own:
+//     every trip of the warp loop runs exactly one CollisionCheckSection frame per busy lane, so a lane that
+//     needs 15 frames for one obstacle does not hold back its 31 neighbours -- they move on to their next
+//     obstacles. The reference's recursion is a per-lane explicit stack of pending [ts, tf] intervals.
+//   * work queue: when enough lanes of a warp have finished their trajectory (ballot + popc) the warp takes
+//     that many new candidates from a global counter with one atomicAdd and the idle lanes build them.
+//   * per-CTA partial verdict counts / best candidate, reduced in block order by k_finalize (deterministic).
+#include "rqcd_device.cuh"
+#include "rqcd_kernels.cuh"
+
+namespace rqcd {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- TMA bulk copy global -> shared (1-D), completion on an mbarrier ---------------------------------
+RQCD_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+RQCD_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+RQCD_DEV void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+RQCD_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RQCD_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RQCD_DONE;\n"
+      "bra RQCD_WAIT;\n"
+      "RQCD_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+RQCD_DEV bool better(double ca, long long ia, double cb, long long ib) {
+  // candidate a beats b: lower cost, or equal cost and lower index; an empty slot has index -1
+  if (ia < 0) return false;
+  if (ib < 0) return true;
+  return ca < cb || (ca == cb && ia < ib);
+}
+
+// ---- trajectory construction for one lane ------------------------------------------------------------
+template <int MODE>
+RQCD_DEV void load_trajectory(const CheckParams& p, long long i, double (&c)[18], double& t0, double& t1,
+                              double& cost) {
+  if (MODE == MODE_BC) {
+    const double* d = p.in;
+    const long long s = p.in_stride;
+    const double Tf = d[18 * s + i];
+    double total = 0.0;
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+      const double p0 = d[(0 + ax) * s + i], v0 = d[(3 + ax) * s + i], a0 = d[(6 + ax) * s + i];
+      const double pf = d[(9 + ax) * s + i], vf = d[(12 + ax) * s + i], af = d[(15 + ax) * s + i];
+      const AxisParams q = gen_axis(p0, v0, a0, pf, vf, af, (p.goal_mask >> (3 * ax)) & 1,
+                                    (p.goal_mask >> (3 * ax + 1)) & 1, (p.goal_mask >> (3 * ax + 2)) & 1, Tf);
+      axis_coeffs(q, p0, v0, a0, c[0 + ax], c[3 + ax], c[6 + ax], c[9 + ax], c[12 + ax], c[15 + ax]);
+      total = (ax == 0) ? q.cost : total + q.cost;  // GetCost: cost[0] + cost[1] + cost[2] (.hpp:214-216)
+    }
+    cost = total;
+    t0 = 0.0;
+    t1 = Tf;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 18; j++) c[j] = p.in[j * p.in_stride + i];
+    t0 = p.t_start ? p.t_start[i] : 0.0;
+    t1 = p.t_end[i];
+    cost = p.cost_in ? p.cost_in[i] : __longlong_as_double(0x7ff8000000000000ll);
+  }
+}
+
+template <int MODE, bool MOVING, bool PAIRWISE>
+__global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kWarps = kThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = PAIRWISE ? 1 : p.m, mp = p.mp;
+
+  double* tab = reinterpret_cast<double*>(smem_raw);
+  int* oflags = reinterpret_cast<int*>(tab + (size_t)p.nfields * mp);
+  unsigned long long* wcnt = reinterpret_cast<unsigned long long*>(oflags + mp);  // [kWarps][8]
+  double* bcost = reinterpret_cast<double*>(wcnt + kWarps * 8);                   // [kThreads]
+  long long* bidx = reinterpret_cast<long long*>(bcost + kThreads);               // [kThreads]
+  double* base = reinterpret_cast<double*>(bidx + kThreads);                      // MOVING: [18][kThreads]
+  __shared__ __align__(8) uint64_t mbar;
+
+  const uint32_t blob_bytes = (uint32_t)(((size_t)p.nfields * mp) * 8 + (size_t)mp * 4);
+  if (tid == 0) mbar_init(&mbar, 1);
+  if (tid < kWarps * 8) wcnt[tid] = 0ull;
+  bcost[tid] = __longlong_as_double(0x7ff0000000000000ll);
+  bidx[tid] = -1;
+  __syncthreads();
+  if (blob_bytes > 0 && !PAIRWISE) {
+    if (tid == 0) tma_bulk_g2s(tab, p.obs_blob, blob_bytes, &mbar);
+    mbar_wait(&mbar, 0);
+  }
+
+  // ---- lane state
+  bool have = false, in_pair = false, exhausted = false;
+  long long idx = 0;
+  double c[18];
+  double t0 = 0, t1 = 0, cost = 0, ts = 0, tf = 0;
+  int k = 0, verdict = 0, first = -1, sp = 0;
+  double2 stack[kMaxDepth];
+  LaneSphere sph;
+  sph.cx = sph.cy = sph.cz = sph.r = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (;;) {
+    // ---- work queue: idle lanes take new candidates
+    const unsigned need = __ballot_sync(kFull, !have);
+    if (need != 0 && !exhausted) {
+      const int cnt = __popc(need);
+      if (cnt >= p.refill_min || need == kFull) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(p.work_counter, (unsigned long long)cnt);
+        b = __shfl_sync(kFull, b, 0);
+        if (b + (unsigned long long)cnt >= (unsigned long long)p.n) exhausted = true;
+        if (!have) {
+          const long long i = (long long)b + __popc(need & lt_mask);
+          if (i < p.n) {
+            idx = i;
+            load_trajectory<MODE>(p, i, c, t0, t1, cost);
+            if (MODE == MODE_BC) {
+              if (p.cost) p.cost[i] = cost;
+              if (p.coeffs) {
+#pragma unroll
+                for (int j = 0; j < 18; j++) p.coeffs[j * p.coeff_stride + i] = c[j];
+              }
+            }
+            if (MOVING) {
+#pragma unroll
+              for (int j = 0; j < 18; j++) base[j * kThreads + tid] = c[j];
+            }
+            if (PAIRWISE) {
+              sph.cx = p.spheres[i];
+              sph.cy = p.spheres[p.sphere_stride + i];
+              sph.cz = p.spheres[2 * p.sphere_stride + i];
+              sph.r = p.spheres[3 * p.sphere_stride + i];
+            }
+            have = true;
+            in_pair = false;
+            k = 0;
+            verdict = 0;
+            first = -1;
+          }
+        }
+      }
+    }
+    if (exhausted && __ballot_sync(kFull, have) == 0) break;
+
+    int pv = -1;  // verdict of the pair that completed in this trip, if any
+
+    // ---- CollisionChecker::CollisionCheck entry for the lane's next obstacle (CollisionChecker.cpp:70-80)
+    if (have && !in_pair && k < m) {
+      ts = t0;
+      tf = t1;
+      bool inside;
+      if (PAIRWISE) {
+        inside = is_inside(sph, traj_value(c, ts)) || is_inside(sph, traj_value(c, tf));
+      } else {
+        TableObs o;
+        o.tab = tab;
+        o.mp = mp;
+        o.k = k;
+        o.flags = oflags[k];
+        if (MOVING) {
+          // Trajectory::operator- (Trajectory.hpp:121-128): coefficient-wise difference on the common window
+          if (o.flags & OBS_MOVING) {
+#pragma unroll
+            for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid] - o.f(OF_MOTION + j);
+            const double ms = o.f(OF_MT0), me = o.f(OF_MT1);
+            ts = (t0 < ms) ? ms : t0;  // std::max(_startTime, rhs start)
+            tf = (me < t1) ? me : t1;  // std::min(_endTime, rhs end)
+          } else {
+#pragma unroll
+            for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid];
+          }
+        }
+        if (MOVING && !(ts <= tf)) {
+          pv = 0;  // no common time (the reference would assert, Trajectory.hpp:68): nothing to hit
+          inside = false;
+        } else {
+          inside = is_inside(o, traj_value(c, ts)) || is_inside(o, traj_value(c, tf));
+        }
+      }
+      if (pv < 0) {
+        if (inside) {
+          pv = 1;
+        } else {
+          in_pair = true;
+          sp = 0;
+        }
+      }
+    }
+
+    // ---- one CollisionCheckSection frame (CollisionChecker.cpp:82-193)
+    if (in_pair) {
+      Children ch;
+      int r;
+      if (PAIRWISE) {
+        r = section_step(c, ts, tf, sph, p.min_t, ch);
+      } else {
+        TableObs o;
+        o.tab = tab;
+        o.mp = mp;
+        o.k = k;
+        o.flags = oflags[k];
+        r = section_step(c, ts, tf, o, p.min_t, ch);
+      }
+      if (r == STEP_CHILD) {
+        if (ch.has_hi) {
+          if (ch.has_lo) {  // the parent's low tail call waits until the high subtree is clear
+            if (sp < kMaxDepth) {
+              stack[sp++] = make_double2(ts, ch.lo_tf);
+            } else {
+              pv = 3;
+              in_pair = false;
+            }
+          }
+          ts = ch.hi_ts;
+        } else {
+          tf = ch.lo_tf;
+        }
+      } else if (r == STEP_CLEAR) {
+        if (sp > 0) {
+          const double2 e = stack[--sp];
+          ts = e.x;
+          tf = e.y;
+        } else {
+          pv = 0;
+          in_pair = false;
+        }
+      } else {
+        pv = r;
+        in_pair = false;
+      }
+    }
+
+    // ---- bookkeeping for completed pairs / trajectories
+    if (pv >= 0) {
+      if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)pv;
+      if (pv != 0 && first < 0) {
+        verdict = pv;
+        first = k;
+      }
+      k++;
+    }
+    const bool fin = have && !in_pair && (k >= m || (p.early_exit && verdict != 0));
+    const int tv = fin ? verdict : -1;
+    {
+      const unsigned p0 = __ballot_sync(kFull, pv == 0), p1 = __ballot_sync(kFull, pv == 1);
+      const unsigned p2 = __ballot_sync(kFull, pv == 2), p3 = __ballot_sync(kFull, pv == 3);
+      const unsigned q0 = __ballot_sync(kFull, tv == 0), q1 = __ballot_sync(kFull, tv == 1);
+      const unsigned q2 = __ballot_sync(kFull, tv == 2), q3 = __ballot_sync(kFull, tv == 3);
+      if (lane == 0) {
+        unsigned long long* w = wcnt + warp * 8;
+        w[0] += __popc(q0);
+        w[1] += __popc(q1);
+        w[2] += __popc(q2);
+        w[3] += __popc(q3);
+        w[4] += __popc(p0);
+        w[5] += __popc(p1);
+        w[6] += __popc(p2);
+        w[7] += __popc(p3);
+      }
+    }
+    if (fin) {
+      if (p.verdict) p.verdict[idx] = (uint8_t)verdict;
+      if (p.first_obstacle) p.first_obstacle[idx] = first;
+      if (verdict == 0 && cost < bcost[tid]) {  // indices handed to one lane ascend, so ties keep the lowest
+        bcost[tid] = cost;
+        bidx[tid] = p.index_base + idx;
+      }
+      have = false;
+    }
+  }
+
+  // ---- CTA partial
+  __syncthreads();
+  if (warp == 0) {
+    double bc = __longlong_as_double(0x7ff0000000000000ll);
+    long long bi = -1;
+    for (int j = lane; j < kThreads; j += 32) {
+      if (better(bcost[j], bidx[j], bc, bi)) {
+        bc = bcost[j];
+        bi = bidx[j];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double oc = __shfl_down_sync(kFull, bc, off);
+      const long long oi = __shfl_down_sync(kFull, bi, off);
+      if (better(oc, oi, bc, bi)) {
+        bc = oc;
+        bi = oi;
+      }
+    }
+    BlockPartial* out = p.partials + blockIdx.x;
+    if (lane < 8) {
+      unsigned long long s = 0;
+      for (int w = 0; w < kWarps; w++) s += wcnt[w * 8 + lane];
+      if (lane < 4) out->traj[lane] = s;
+      else out->pair[lane - 4] = s;
+    }
+    if (lane == 0) {
+      out->best_cost = bc;
+      out->best_index = bi;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int nparts, DevSummary* out) {
+  __shared__ unsigned long long cnt[8];
+  __shared__ double scost[256];
+  __shared__ long long sidx[256];
+  const int tid = threadIdx.x;
+  if (tid < 8) cnt[tid] = 0ull;
+  double bc = __longlong_as_double(0x7ff0000000000000ll);
+  long long bi = -1;
+  unsigned long long loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = tid; j < nparts; j += blockDim.x) {
+    for (int v = 0; v < 4; v++) {
+      loc[v] += parts[j].traj[v];
+      loc[4 + v] += parts[j].pair[v];
+    }
+    if (better(parts[j].best_cost, parts[j].best_index, bc, bi)) {
+      bc = parts[j].best_cost;
+      bi = parts[j].best_index;
+    }
+  }
+  scost[tid] = bc;
+  sidx[tid] = bi;
+  __syncthreads();
+  for (int v = 0; v < 8; v++)
+    if (loc[v]) atomicAdd(&cnt[v], loc[v]);
+  __syncthreads();
+  if (tid == 0) {
+    for (int j = 1; j < (int)blockDim.x; j++)
+      if (better(scost[j], sidx[j], bc, bi)) {
+        bc = scost[j];
+        bi = sidx[j];
+      }
+    for (int v = 0; v < 4; v++) {
+      out->traj[v] = cnt[v];
+      out->pair[v] = cnt[4 + v];
+    }
+    out->pairs_checked = cnt[4] + cnt[5] + cnt[6] + cnt[7];
+    out->best_cost = bc;
+    out->best_index = bi;
+  }
+}
+
+// ---- RapidTrajectoryGenerator::Generate + GetCost + GetTrajectory only --------------------------------
+__global__ void __launch_bounds__(256) k_generate(const double* bc, long long stride, unsigned goal_mask, long long n,
+                                                  double* cost, double* coeffs, long long coeff_stride) {
+  CheckParams p = {};
+  p.in = bc;
+  p.in_stride = stride;
+  p.goal_mask = goal_mask;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double c[18], t0, t1, co;
+    load_trajectory<MODE_BC>(p, i, c, t0, t1, co);
+    if (cost) cost[i] = co;
+    if (coeffs) {
+#pragma unroll
+      for (int j = 0; j < 18; j++) coeffs[j * coeff_stride + i] = c[j];
+    }
+  }
+}
+
+// ---- solver unit kernels (test surface of Quartic::solveP3 / solve_quartic) ---------------------------
+__global__ void __launch_bounds__(256) k_solve(bool quartic, const double* coef, long long n, double* roots, int* count) {
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (quartic) {
+      double r0 = nan, r1 = nan, r2 = nan, r3 = nan;
+      count[i] = solve_quartic(coef[i], coef[n + i], coef[2 * n + i], coef[3 * n + i], r0, r1, r2, r3);
+      roots[i] = r0;
+      roots[n + i] = r1;
+      roots[2 * n + i] = r2;
+      roots[3 * n + i] = r3;
+    } else {
+      double x0 = nan, x1 = nan, x2 = nan;
+      count[i] = solve_p3(coef[i], coef[n + i], coef[2 * n + i], x0, x1, x2);
+      roots[i] = x0;
+      roots[n + i] = x1;
+      roots[2 * n + i] = x2;
+    }
+  }
+}
+
+// ---- synthetic boundary conditions: splitmix64 of (seed, row, global index); ranges of
+// test/PerformanceEval.cpp:59-65 (pos0 = 0, everything else U(-4,4), Tf U(0.2,4)) ------------------------
+RQCD_DEV unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) k_synth_bc(unsigned long long seed, long long index_base, long long n,
+                                                  double* bc, long long stride) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long g = (unsigned long long)(index_base + i);
+#pragma unroll
+    for (int r = 0; r < 19; r++) {
+      const unsigned long long h = splitmix64(splitmix64(seed ^ ((unsigned long long)r * 0xD6E8FEB86659FD93ull)) + g);
+      const double u = (double)(h >> 11) * 0x1.0p-53;
+      double v;
+      if (r < 3) v = 0.0;
+      else if (r == 18) v = 0.2 + u * (4.0 - 0.2);
+      else v = -4.0 + u * 8.0;
+      bc[r * stride + i] = v;
+    }
+  }
+}
+
+// ---- FP64 issue ceilings: dependent-free DFMA chains, and DMUL+DADD chains (what -fmad=false code issues) --
+template <bool FMA>
+__global__ void __launch_bounds__(kPeakThreads) k_fp64_peak(int iters, double* sink) {
+  double a[kPeakChains];
+  const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-9;
+#pragma unroll
+  for (int j = 0; j < kPeakChains; j++) a[j] = 1.0 + j;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < kPeakInnerOps; u++) {
+#pragma unroll
+      for (int j = 0; j < kPeakChains; j++) {
+        if (FMA) a[j] = __fma_rn(a[j], x, y);
+        else a[j] = (u & 1) ? __dadd_rn(a[j], y) : __dmul_rn(a[j], x);
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int j = 0; j < kPeakChains; j++) s += a[j];
+  if (s == 123.456) sink[0] = s;
+}
+
+template <int MODE, bool MOVING, bool PAIRWISE>
+const void* check_fn() {
+  return reinterpret_cast<const void*>(&k_check<MODE, MOVING, PAIRWISE>);
+}
+
+const void* select_check(int mode, bool moving, bool pairwise) {
+  if (pairwise) return check_fn<MODE_BC, false, true>();
+  if (mode == MODE_BC) return moving ? check_fn<MODE_BC, true, false>() : check_fn<MODE_BC, false, false>();
+  return moving ? check_fn<MODE_COEFF, true, false>() : check_fn<MODE_COEFF, false, false>();
+}
+
+int grid_for(long long n, int cap) {
+  long long b = (n + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+}  // namespace
+
+size_t check_smem_bytes(int mp, int nfields, bool moving) {
+  size_t b = (size_t)nfields * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
+  b += (kThreads / 32) * 8 * 8;                           // warp counters
+  b += (size_t)kThreads * 16;                             // best cost / index per thread
+  if (moving) b += (size_t)18 * kThreads * 8;             // the lane's own coefficients
+  return b;
+}
+
+cudaError_t check_prepare(int mode, bool moving, bool pairwise, size_t smem) {
+  return cudaFuncSetAttribute(select_check(mode, moving, pairwise), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)smem);
+}
+
+int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, size_t smem) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, select_check(mode, moving, pairwise), kThreads, smem) !=
+      cudaSuccess)
+    return 0;
+  return nb;
+}
+
+cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
+                         DevSummary* d_summary) {
+  const size_t smem = check_smem_bytes(pairwise ? 0 : p.mp, pairwise ? 0 : p.nfields, moving);
+  cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  CheckParams q = p;
+  if (pairwise) {
+    q.mp = 0;
+    q.nfields = 0;
+  }
+  void* args[] = {&q};
+  e = cudaLaunchKernel(select_check(mode, moving, pairwise), dim3(grid), dim3(kThreads), args, smem, s);
+  if (e != cudaSuccess) return e;
+  k_finalize<<<1, 256, 0, s>>>(p.partials, grid, d_summary);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_generate(const double* bc, long long stride, unsigned goal_mask, long long n, double* cost,
+                            double* coeffs, long long coeff_stride, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_generate<<<grid_for(n, 148 * 8), 256, 0, s>>>(bc, stride, goal_mask, n, cost, coeffs, coeff_stride);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_solve(bool quartic, const double* coef, long long n, double* roots, int* count, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_solve<<<grid_for(n, 148 * 8), 256, 0, s>>>(quartic, coef, n, roots, count);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_synth_bc(unsigned long long seed, long long index_base, long long n, double* bc, long long stride,
+                            cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_synth_bc<<<grid_for(n, 148 * 8), 256, 0, s>>>(seed, index_base, n, bc, stride);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_peak(bool fma, int blocks, int iters, double* sink, cudaStream_t s) {
+  if (fma) k_fp64_peak<true><<<blocks, kPeakThreads, 0, s>>>(iters, sink);
+  else k_fp64_peak<false><<<blocks, kPeakThreads, 0, s>>>(iters, sink);
+  return cudaGetLastError();
+}
+
+}  // namespace rqcd

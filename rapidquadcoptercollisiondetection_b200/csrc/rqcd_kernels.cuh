@@ -1,0 +1,77 @@
+// rqcd_kernels.cuh -- launch-side declarations shared by rqcd_kernels.cu (device code, compiled with
+// -fmad=false) and rqcd_api.cu (C ABI, host logic).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rqcd {
+
+constexpr int kThreads = 256;     // threads per CTA of the check kernel
+constexpr int kMaxDepth = 40;     // RQCD_MAX_DEPTH: pending intervals per check
+
+// One CTA's contribution to rqcd_summary; reduced by k_finalize in block order (deterministic).
+struct BlockPartial {
+  unsigned long long traj[4];
+  unsigned long long pair[4];
+  double best_cost;
+  long long best_index;
+};
+
+struct DevSummary {  // mirrors rqcd_summary
+  unsigned long long traj[4];
+  unsigned long long pair[4];
+  unsigned long long pairs_checked;
+  double best_cost;
+  long long best_index;
+};
+
+enum CheckMode { MODE_BC = 0, MODE_COEFF = 1 };
+
+struct CheckParams {
+  // trajectories
+  const double* in;        // MODE_BC: 19 boundary-condition rows; MODE_COEFF: 18 coefficient rows
+  long long in_stride;
+  const double* t_start;   // MODE_COEFF, may be null (0)
+  const double* t_end;     // MODE_COEFF
+  const double* cost_in;   // MODE_COEFF, may be null (NaN)
+  const double* spheres;   // pairwise: 4 rows cx, cy, cz, radius
+  long long sphere_stride;
+  unsigned goal_mask;
+  long long n;
+  long long index_base;
+  double min_t;
+  // obstacle table blob in global memory: nfields*mp doubles followed by mp int flags
+  const void* obs_blob;
+  int m, mp, nfields;
+  // outputs, each may be null
+  uint8_t* verdict;
+  int* first_obstacle;
+  uint8_t* verdict_matrix;
+  double* cost;
+  double* coeffs;
+  long long coeff_stride;
+  // control
+  int early_exit;
+  int refill_min;          // idle lanes per warp that trigger a work-queue fetch
+  unsigned long long* work_counter;
+  BlockPartial* partials;  // [gridDim.x]
+};
+
+size_t check_smem_bytes(int mp, int nfields, bool moving);
+// Returns the number of kernels launched (2: check + finalize) or a negative cudaError.
+cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
+                         DevSummary* d_summary);
+int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, size_t smem);
+cudaError_t check_prepare(int mode, bool moving, bool pairwise, size_t smem);  // opt in to large dynamic smem
+
+cudaError_t launch_generate(const double* bc, long long stride, unsigned goal_mask, long long n, double* cost,
+                            double* coeffs, long long coeff_stride, cudaStream_t s);
+cudaError_t launch_solve(bool quartic, const double* coef, long long n, double* roots, int* count, cudaStream_t s);
+cudaError_t launch_synth_bc(unsigned long long seed, long long index_base, long long n, double* bc, long long stride,
+                            cudaStream_t s);
+cudaError_t launch_fp64_peak(bool fma, int blocks, int iters, double* sink, cudaStream_t s);
+constexpr int kPeakThreads = 256;
+constexpr int kPeakChains = 8;      // independent accumulators per thread
+constexpr int kPeakInnerOps = 64;   // operations per chain per outer iteration
+
+}  // namespace rqcd

@@ -1,0 +1,185 @@
+"""GPU: the CUDA path, called through the C ABI (librqcd.so), against the committed reference vectors
+(tests/golden/) and against the CPU oracle on the same seeded inputs. Verdicts, first-hit indices, counts and
+best-candidate indices are compared bit-exact; coefficients, costs and roots within 1e-9 relative
+(BASELINE.json), written in tests/util.py."""
+import numpy as np
+import pytest
+
+from rapidquadcoptercollisiondetection_b200 import abi, workloads as W
+from tests.util import assert_close, assert_roots_match, obstacles_from
+
+pytestmark = pytest.mark.gpu
+MIN_T = 0.002
+
+
+def test_device_is_blackwell(ctx):
+    info = ctx.device_info()
+    assert info["cc"][0] >= 10 and info["sm_count"] > 0
+
+
+def test_static_set_matches_reference_vectors(ctx, vectors):
+    obs, m = obstacles_from(vectors, "st_obs_")
+    ctx.set_obstacles(obs, m)
+    bc = W.synth_bc(int(vectors["st_seed"]), 0, int(vectors["st_n"]))
+    before = ctx.launch_count()
+    r = ctx.generate_check(bc, MIN_T)
+    assert ctx.launch_count() == before + 2
+    assert r["status"] == abi.OK
+    np.testing.assert_array_equal(r["verdict_matrix"], vectors["st_matrix"])
+    np.testing.assert_array_equal(r["verdict"], vectors["st_verdict"])
+    np.testing.assert_array_equal(r["first_obstacle"], vectors["st_first"])
+    assert_close(r["cost"], vectors["st_cost"], what="cost")
+    assert_close(r["coeffs"], vectors["st_coeffs"], what="coeffs")
+    s = r["summary"]
+    assert s["best_index"] == int(vectors["st_best_index"])
+    assert s["pairs_checked"] == bc.shape[1] * m
+    assert s["pair_counts"][:3] == [int((vectors["st_matrix"] == v).sum()) for v in range(3)]
+    assert s["traj_counts"][:3] == [int((vectors["st_verdict"] == v).sum()) for v in range(3)]
+
+
+def test_early_exit_is_the_forest_loop(ctx, vectors, oracle):
+    """ForestPerformanceEval.cpp:216-225: stop at the first obstacle whose check is not NoCollision."""
+    obs, m = obstacles_from(vectors, "st_obs_")
+    ctx.set_obstacles(obs, m)
+    bc = W.synth_bc(int(vectors["st_seed"]), 0, int(vectors["st_n"]))
+    r = ctx.generate_check(bc, MIN_T, flags=abi.F_EARLY_EXIT)
+    o = oracle.generate_check(bc, obs, m, MIN_T, flags=abi.F_EARLY_EXIT, matrix=False)
+    np.testing.assert_array_equal(r["verdict"], vectors["st_verdict"])
+    np.testing.assert_array_equal(r["first_obstacle"], vectors["st_first"])
+    assert r["summary"]["pairs_checked"] == o["summary"]["pairs_checked"]
+    assert r["summary"]["pair_counts"] == o["summary"]["pair_counts"]
+
+
+def test_forest_driver_vectors(ctx, vectors, forest_golden):
+    """Batch stream of ForestPerformanceEval (ref_c2_run) incl. batch 0 = data/ForestPerfEval.csv."""
+    ctx.set_obstacles(abi.make_obstacles(W.forest_obstacles()), 5)
+    bc = vectors["c2_bc"]
+    r = ctx.generate_check(bc, MIN_T, flags=abi.F_EARLY_EXIT)
+    np.testing.assert_array_equal(r["verdict"], vectors["c2_verdict"])
+    assert r["summary"]["pairs_checked"] == int(vectors["c2_pairs"])
+    csv = forest_golden["csv"]
+    np.testing.assert_array_equal(r["verdict"][:100], csv[:, 20].astype(np.uint8))
+    np.testing.assert_allclose(r["coeffs"][:, :100].T, csv[:, :18], rtol=2e-5, atol=1e-6)
+
+
+def test_performance_eval_driver_vectors(ctx, vectors):
+    """Trial stream of PerformanceEval (ref_c1_run): trajectory i against its own sphere i."""
+    r = ctx.generate_check_pairwise(vectors["c1_bc"], vectors["c1_spheres"], MIN_T)
+    np.testing.assert_array_equal(r["verdict"], vectors["c1_verdict"])
+    n = vectors["c1_bc"].shape[1]
+    assert r["summary"]["pairs_checked"] == n and sum(r["summary"]["traj_counts"]) == n
+
+
+def test_goal_flag_combinations(ctx, vectors):
+    bc = W.synth_bc(int(vectors["gm_seed"]), 0, int(vectors["gm_n"]))
+    for j, mask in enumerate(vectors["gm_masks"]):
+        g = ctx.generate(bc, int(mask))
+        assert_close(g["cost"], vectors[f"gm_cost_{j}"], what=f"cost mask {int(mask):#x}")
+        assert_close(g["coeffs"], vectors[f"gm_coeffs_{j}"], what=f"coeffs mask {int(mask):#x}")
+
+
+def test_moving_obstacles_match_reference_vectors(ctx, vectors):
+    obs, m = obstacles_from(vectors, "mv_obs_")
+    ctx.set_obstacles(obs, m)
+    bc = W.synth_bc(int(vectors["mv_seed"]), 0, int(vectors["mv_n"]))
+    r = ctx.generate_check(bc, MIN_T)
+    np.testing.assert_array_equal(r["verdict_matrix"], vectors["mv_matrix"])
+    np.testing.assert_array_equal(r["verdict"], vectors["mv_verdict"])
+    np.testing.assert_array_equal(r["first_obstacle"], vectors["mv_first"])
+
+
+def test_prebuilt_quintics_with_windows(ctx, vectors):
+    obs, m = obstacles_from(vectors, "ck_obs_")
+    ctx.set_obstacles(obs, m)
+    r = ctx.check(vectors["ck_coeffs"], vectors["ck_t_end"], MIN_T, t_start=vectors["ck_t_start"], cost=vectors["ck_cost"])
+    np.testing.assert_array_equal(r["verdict_matrix"], vectors["ck_matrix"])
+    np.testing.assert_array_equal(r["verdict"], vectors["ck_verdict"])
+    assert r["summary"]["best_index"] == int(vectors["ck_best_index"])
+
+
+def test_solver_vectors(ctx, vectors):
+    roots, cnt = ctx.solve_quartic(vectors["sq_coef"])
+    assert_roots_match(vectors["sq_coef"], roots, cnt, vectors["sq_roots"], vectors["sq_count"], "quartic")
+    roots, cnt = ctx.solve_cubic(vectors["sc_coef"])
+    assert_roots_match(vectors["sc_coef"], roots, cnt, vectors["sc_roots"], vectors["sc_count"], "cubic")
+
+
+def test_solver_random_against_oracle(ctx, oracle):
+    rng = np.random.default_rng(9)
+    q = np.concatenate([rng.uniform(-10, 10, (4, 200_000)), rng.normal(0, 100, (4, 50_000))], axis=1)
+    ra, ca = ctx.solve_quartic(q)
+    rb, cb = oracle.solve_quartic(q)
+    assert_roots_match(q, ra, ca, rb, cb, "quartic")
+    c = rng.uniform(-10, 10, (3, 200_000))
+    ra, ca = ctx.solve_cubic(c)
+    rb, cb = oracle.solve_cubic(c)
+    assert_roots_match(c, ra, ca, rb, cb, "cubic")
+
+
+@pytest.mark.parametrize("n,ns,npz,seed", [(20_000, 32, 32, 101), (50_000, 5, 0, 102), (3_000, 0, 40, 103), (777, 1, 0, 104)])
+def test_random_sets_against_oracle(ctx, oracle, n, ns, npz, seed):
+    """Same seeded inputs through the CUDA path and the oracle: every pair's verdict, first hits, counts, best."""
+    specs = W.static_obstacles(seed, ns, npz)
+    obs = abi.make_obstacles(specs)
+    m = len(specs)
+    ctx.set_obstacles(obs, m)
+    bc = W.synth_bc(seed, 12345, n)
+    r = ctx.generate_check(bc, MIN_T, index_base=12345)
+    o = oracle.generate_check(bc, obs, m, MIN_T, index_base=12345, nthreads=8)
+    np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"])
+    np.testing.assert_array_equal(r["verdict"], o["verdict"])
+    np.testing.assert_array_equal(r["first_obstacle"], o["first_obstacle"])
+    assert_close(r["cost"], o["cost"], what="cost")
+    assert_close(r["coeffs"], o["coeffs"], what="coeffs")
+    assert r["summary"]["traj_counts"] == o["summary"]["traj_counts"]
+    assert r["summary"]["pair_counts"] == o["summary"]["pair_counts"]
+    assert r["summary"]["best_index"] == o["summary"]["best_index"]
+    assert_close(r["summary"]["best_cost"], o["summary"]["best_cost"], what="best cost")
+
+
+def test_edge_cases(ctx, oracle):
+    """Empty batch, empty obstacle set, a one-trajectory batch, ragged strides, invalid arguments."""
+    specs = W.static_obstacles(5, 2, 2)
+    ctx.set_obstacles(abi.make_obstacles(specs), 4)
+    r = ctx.generate_check(np.zeros((abi.BC_ROWS, 0)), MIN_T)
+    assert r["summary"]["pairs_checked"] == 0 and r["summary"]["best_index"] == -1
+    bc = W.synth_bc(6, 0, 1)
+    r = ctx.generate_check(bc, MIN_T)
+    o = oracle.generate_check(bc, abi.make_obstacles(specs), 4, MIN_T)
+    np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"])
+    ctx.set_obstacles(abi.make_obstacles([]), 0)
+    bc = W.synth_bc(6, 0, 100)
+    r = ctx.generate_check(bc, MIN_T, matrix=False)
+    assert r["summary"]["traj_counts"][0] == 100 and (r["verdict"] == 0).all() and (r["first_obstacle"] == -1).all()
+    # minT <= 0 would make the reference recurse without bound: rejected
+    from rapidquadcoptercollisiondetection_b200.api import RqcdError
+    with pytest.raises(RqcdError):
+        ctx.generate_check(bc, 0.0)
+    with pytest.raises(RqcdError):
+        ctx.set_obstacles(abi.make_obstacles([{"type": "sphere", "center": [0, 0, 0], "radius": -1.0}]), 1)
+
+
+def test_indeterminable_and_deep_recursion(ctx, oracle):
+    """Trajectories grazing a sphere: long recursions, Indeterminable verdicts, small minT (deep stacks)."""
+    n = 4096
+    rng = np.random.default_rng(3)
+    bc = np.zeros((abi.BC_ROWS, n))
+    # straight-ish lines passing at distance ~r from the origin
+    bc[abi.BC_P0 + 0] = -3.0
+    bc[abi.BC_P0 + 1] = 1.0 + rng.normal(0, 1e-7, n)
+    bc[abi.BC_V0 + 0] = 2.0
+    bc[abi.BC_PF + 0] = 3.0
+    bc[abi.BC_PF + 1] = 1.0 + rng.normal(0, 1e-7, n)
+    bc[abi.BC_VF + 0] = 2.0
+    bc[abi.BC_TF] = 3.0
+    specs = [{"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 1.0},
+             {"type": "prism", "center": [0.0, 2.0, 0.0], "side": [1.0, 2.0, 1.0], "quat": [1.0, 0, 0, 0]}]
+    obs = abi.make_obstacles(specs)
+    ctx.set_obstacles(obs, 2)
+    for min_t in (0.002, 1e-6, 1e-9):
+        r = ctx.generate_check(bc, min_t)
+        o = oracle.generate_check(bc, obs, 2, min_t, nthreads=8)
+        np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"])
+        assert r["summary"]["pair_counts"] == o["summary"]["pair_counts"]
+        assert r["status"] == abi.OK
+    assert (o["verdict_matrix"] == 2).any() or (o["verdict_matrix"] == 1).any()
