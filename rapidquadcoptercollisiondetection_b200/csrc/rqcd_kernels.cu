@@ -8,9 +8,11 @@
 //   * persistent CTAs (grid = SMs x resident CTAs); the prepared obstacle table is staged once per CTA into
 //     shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) and reused by every candidate.
 //   * a lane owns one trajectory (its 18 coefficients live in registers) and walks the obstacles on its own:
-//     every trip of the warp loop runs exactly one CollisionCheckSection frame per busy lane, so a lane that
+//     every trip of the warp loop runs exactly one CollisionCheckSection frame per lane, so a lane that
 //     needs 15 frames for one obstacle does not hold back its 31 neighbours -- they move on to their next
 //     obstacles. The reference's recursion is a per-lane explicit stack of pending [ts, tf] intervals.
+//   * the frame is one converged instruction stream for the whole warp (see frame() in rqcd_device.cuh): the
+//     only divergent regions are the sphere/prism arithmetic and the transcendental core of the cubic solver.
 //   * work queue: when enough lanes of a warp have finished their trajectory (ballot + popc) the warp takes
 //     that many new candidates from a global counter with one atomicAdd and the idle lanes build them.
 //   * per-CTA partial verdict counts / best candidate, reduced in block order by k_finalize (deterministic).
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
   }
 
   // ---- lane state
-  bool have = false, in_pair = false, exhausted = false;
+  bool have = false, in_pair = false, exhausted = false, first_frame = false;
   long long idx = 0;
   double c[18];
   double t0 = 0, t1 = 0, cost = 0, ts = 0, tf = 0;
@@ -170,89 +172,78 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
 
     int pv = -1;  // verdict of the pair that completed in this trip, if any
 
-    // ---- CollisionChecker::CollisionCheck entry for the lane's next obstacle (CollisionChecker.cpp:70-80)
+    // ---- CollisionChecker::CollisionCheck entry for the lane's next obstacle (CollisionChecker.cpp:70-80);
+    // its end-point tests ride on the first frame below
     if (have && !in_pair && k < m) {
       ts = t0;
       tf = t1;
-      bool inside;
-      if (PAIRWISE) {
-        inside = is_inside(sph, traj_value(c, ts)) || is_inside(sph, traj_value(c, tf));
-      } else {
-        TableObs o;
-        o.tab = tab;
-        o.mp = mp;
-        o.k = k;
-        o.flags = oflags[k];
-        if (MOVING) {
-          // Trajectory::operator- (Trajectory.hpp:121-128): coefficient-wise difference on the common window
-          if (o.flags & OBS_MOVING) {
+      in_pair = true;
+      first_frame = true;
+      sp = 0;
+      if (MOVING) {
+        // Trajectory::operator- (Trajectory.hpp:121-128): coefficient-wise difference on the common window
+        const int fl = oflags[k];
+        if (fl & OBS_MOVING) {
 #pragma unroll
-            for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid] - o.f(OF_MOTION + j);
-            const double ms = o.f(OF_MT0), me = o.f(OF_MT1);
-            ts = (t0 < ms) ? ms : t0;  // std::max(_startTime, rhs start)
-            tf = (me < t1) ? me : t1;  // std::min(_endTime, rhs end)
-          } else {
-#pragma unroll
-            for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid];
+          for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid] - tab[(OF_MOTION + j) * mp + k];
+          const double ms = tab[OF_MT0 * mp + k], me = tab[OF_MT1 * mp + k];
+          ts = (t0 < ms) ? ms : t0;  // std::max(_startTime, rhs start)
+          tf = (me < t1) ? me : t1;  // std::min(_endTime, rhs end)
+          if (!(ts <= tf)) {  // no common time (the reference would assert, Trajectory.hpp:68): nothing to hit
+            pv = 0;
+            in_pair = false;
           }
-        }
-        if (MOVING && !(ts <= tf)) {
-          pv = 0;  // no common time (the reference would assert, Trajectory.hpp:68): nothing to hit
-          inside = false;
         } else {
-          inside = is_inside(o, traj_value(c, ts)) || is_inside(o, traj_value(c, tf));
-        }
-      }
-      if (pv < 0) {
-        if (inside) {
-          pv = 1;
-        } else {
-          in_pair = true;
-          sp = 0;
+#pragma unroll
+          for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid];
         }
       }
     }
 
-    // ---- one CollisionCheckSection frame (CollisionChecker.cpp:82-193)
-    if (in_pair) {
+    // ---- one CollisionCheckSection frame (CollisionChecker.cpp:82-193), executed by the whole warp: lanes
+    // without a pair run it on stale data and drop the result, which keeps the warp converged
+    {
       Children ch;
       int r;
       if (PAIRWISE) {
-        r = section_step(c, ts, tf, sph, p.min_t, ch);
+        r = frame(c, ts, tf, first_frame, sph, p.min_t, ch);
       } else {
         TableObs o;
         o.tab = tab;
         o.mp = mp;
-        o.k = k;
-        o.flags = oflags[k];
-        r = section_step(c, ts, tf, o, p.min_t, ch);
+        o.k = min(k, max(m - 1, 0));
+        o.flags = oflags[o.k];
+        r = frame(c, ts, tf, first_frame, o, p.min_t, ch);
       }
-      if (r == STEP_CHILD) {
-        if (ch.has_hi) {
-          if (ch.has_lo) {  // the parent's low tail call waits until the high subtree is clear
-            if (sp < kMaxDepth) {
-              stack[sp++] = make_double2(ts, ch.lo_tf);
-            } else {
-              pv = 3;
-              in_pair = false;
+      first_frame = false;
+      if (in_pair) {
+        if (r == STEP_CHILD) {
+          if (ch.has_hi) {
+            if (ch.has_lo) {  // the parent's low tail call waits until the high subtree is clear
+              if (sp < kMaxDepth) {
+                stack[sp++] = make_double2(ts, ch.lo_tf);
+              } else {
+                pv = 3;
+                in_pair = false;
+              }
             }
+            ts = ch.hi_ts;
+          } else {
+            tf = ch.lo_tf;
           }
-          ts = ch.hi_ts;
+        } else if (r == STEP_CLEAR) {
+          if (sp > 0) {
+            const double2 e = stack[--sp];
+            ts = e.x;
+            tf = e.y;
+          } else {
+            pv = 0;
+            in_pair = false;
+          }
         } else {
-          tf = ch.lo_tf;
-        }
-      } else if (r == STEP_CLEAR) {
-        if (sp > 0) {
-          const double2 e = stack[--sp];
-          ts = e.x;
-          tf = e.y;
-        } else {
-          pv = 0;
+          pv = r;
           in_pair = false;
         }
-      } else {
-        pv = r;
-        in_pair = false;
       }
     }
 
@@ -391,20 +382,33 @@ __global__ void __launch_bounds__(256) k_generate(const double* bc, long long st
 // ---- solver unit kernels (test surface of Quartic::solveP3 / solve_quartic) ---------------------------
 __global__ void __launch_bounds__(256) k_solve(bool quartic, const double* coef, long long n, double* roots, int* count) {
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  // warp-uniform trip count: the solver reconverges with __syncwarp, so all 32 lanes stay in the loop and
+  // lanes past the end work on a clamped index without storing
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += step) {
+    const long long i = i0 + (threadIdx.x & 31);
+    const bool live = i < n;
+    const long long j = live ? i : n - 1;
     if (quartic) {
       double r0 = nan, r1 = nan, r2 = nan, r3 = nan;
-      count[i] = solve_quartic(coef[i], coef[n + i], coef[2 * n + i], coef[3 * n + i], r0, r1, r2, r3);
-      roots[i] = r0;
-      roots[n + i] = r1;
-      roots[2 * n + i] = r2;
-      roots[3 * n + i] = r3;
+      const int cnt = solve_quartic(coef[j], coef[n + j], coef[2 * n + j], coef[3 * n + j], r0, r1, r2, r3);
+      if (live) {
+        count[i] = cnt;
+        roots[i] = r0;
+        roots[n + i] = r1;
+        roots[2 * n + i] = cnt > 2 ? r2 : nan;
+        roots[3 * n + i] = cnt > 2 ? r3 : nan;
+        if (cnt == 0) roots[i] = roots[n + i] = nan;
+      }
     } else {
       double x0 = nan, x1 = nan, x2 = nan;
-      count[i] = solve_p3(coef[i], coef[n + i], coef[2 * n + i], x0, x1, x2);
-      roots[i] = x0;
-      roots[n + i] = x1;
-      roots[2 * n + i] = x2;
+      const int cnt = solve_p3(coef[j], coef[n + j], coef[2 * n + j], x0, x1, x2);
+      if (live) {
+        count[i] = cnt;
+        roots[i] = x0;
+        roots[n + i] = x1;
+        roots[2 * n + i] = x2;
+      }
     }
   }
 }
