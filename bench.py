@@ -242,8 +242,8 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from rapidquadcoptercollisiondetection_b200 import abi, workloads as W
-    from rapidquadcoptercollisiondetection_b200.api import Context, merge_summaries
+    from rapidquadcoptercollisiondetection_b200 import abi, sharding, workloads as W
+    from rapidquadcoptercollisiondetection_b200.api import Context
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -258,8 +258,7 @@ def main():
     name = args.workload
     w = WORKLOADS[name]
     n_global = w["n"] if w["scaling"] == "strong" else w["n"] * world
-    lo = n_global * rank // world
-    hi = n_global * (rank + 1) // world
+    lo, hi = sharding.shard_range(n_global, rank, world)
     n = hi - lo
 
     ctx = Context(local)
@@ -302,20 +301,7 @@ def main():
 
     def exchange(s):
         """The one exchange step: all-gather of the per-shard summary records over NCCL, merged on every rank."""
-        if world == 1:
-            return s
-        rec = np.zeros(11, dtype=np.int64)
-        rec[0:4] = s["traj_counts"]
-        rec[4:8] = s["pair_counts"]
-        rec[8] = s["pairs_checked"]
-        rec[9] = np.float64(s["best_cost"]).view(np.int64)
-        rec[10] = s["best_index"]
-        mine = torch.from_numpy(rec).to(dev)
-        dist.all_gather_into_tensor(gather_buf, mine)
-        allr = gather_buf.cpu().numpy()
-        shards = [{"traj_counts": r[0:4].tolist(), "pair_counts": r[4:8].tolist(), "pairs_checked": int(r[8]),
-                   "best_cost": float(r[9:10].view(np.float64)[0]), "best_index": int(r[10])} for r in allr]
-        return merge_summaries(shards)
+        return sharding.exchange_summaries(s, dev, gather_buf)
 
     def barrier():
         if world > 1:

@@ -1,0 +1,331 @@
+// rqcd/facade.hpp -- C++ facade over the C ABI (rqcd.h) that keeps the reference's names for the hot path:
+//
+//   CommonMath::Vec3 / Rotation / Boundary / ConvexObj / Sphere / RectPrism / Trajectory   (data holders)
+//   RapidQuadrocopterTrajectoryGenerator::RapidTrajectoryGenerator
+//        ctor(x0, v0, a0, gravity), SetGoal{Position,Velocity,Acceleration}[InAxis], Reset, Generate, GetCost,
+//        GetTrajectory                    (reference: include/RapidQuadcopterTrajectories/RapidTrajectoryGenerator.hpp:77-114, 214-241)
+//   RapidCollisionChecker::CollisionChecker
+//        ctor(Trajectory), CollisionCheck(shared_ptr<ConvexObj>, minTimeSection) -> CollisionResult
+//                                         (reference: include/RapidCollisionDetection/CollisionChecker.hpp:33-61)
+//   rqcd::Batch -- the batched form both drivers' trial loops collapse to (PerformanceEval.cpp:140-182,
+//                  ForestPerformanceEval.cpp:177-225): N candidates x M obstacles in one call.
+//
+// Every method that computes something is one call into librqcd.so, i.e. a kernel launch on the GPU; the
+// single-object methods are batches of one. There is no CPU implementation behind these classes: without a
+// B200 the first call throws rqcd::Error(RQCD_ERR_NO_DEVICE).  The classes hold data only -- evaluating a
+// trajectory, tangent planes etc. on the host is deliberately not offered here.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../rqcd.h"
+
+namespace rqcd {
+
+class Error : public std::runtime_error {
+ public:
+  Error(int status, const std::string& detail)
+      : std::runtime_error(std::string("rqcd: ") + rqcd_strerror(status) + (detail.empty() ? "" : " [" + detail + "]")),
+        status_(status) {}
+  int status() const { return status_; }
+
+ private:
+  int status_;
+};
+
+// RAII owner of one rqcd_ctx (one GPU, one stream).
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    int st = rqcd_create(&ctx_, device);
+    if (st != RQCD_OK) throw Error(st, "rqcd_create");
+  }
+  ~Context() { rqcd_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  rqcd_ctx* get() const { return ctx_; }
+  void check(int st, bool allow_depth_cap = false) const {
+    if (st == RQCD_OK || (allow_depth_cap && st == RQCD_ERR_DEPTH_CAP)) return;
+    throw Error(st, rqcd_last_error(ctx_));
+  }
+  // The context single-object facade calls run on (created on first use, device 0 or $RQCD_DEVICE).
+  static Context& Default() {
+    static Context c(getenv("RQCD_DEVICE") ? atoi(getenv("RQCD_DEVICE")) : 0);
+    return c;
+  }
+
+ private:
+  rqcd_ctx* ctx_ = nullptr;
+};
+
+}  // namespace rqcd
+
+namespace CommonMath {
+
+struct Vec3 {
+  double x, y, z;
+  Vec3() : x(std::numeric_limits<double>::quiet_NaN()), y(x), z(x) {}
+  Vec3(double xi, double yi, double zi) : x(xi), y(yi), z(zi) {}
+  double operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+  double& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
+};
+
+// Unit quaternion (w, x, y, z), local -> global, as Rotation(a, b, c, d) of the reference (Rotation.hpp:42-47).
+struct Rotation {
+  double v[4];
+  Rotation(double a, double b, double c, double d) : v{a, b, c, d} {}
+  static Rotation Identity() { return Rotation(1, 0, 0, 0); }
+  static Rotation FromAxisAngle(const Vec3& unitAxis, double angle) {  // Rotation.hpp:92-97 (parameter set-up only)
+    const double s = std::sin(angle * 0.5);
+    return Rotation(std::cos(angle * 0.5), s * unitAxis.x, s * unitAxis.y, s * unitAxis.z);
+  }
+};
+
+struct Boundary {  // ConvexObj.hpp:29-53
+  Vec3 point, normal;
+};
+
+// The reference's ConvexObj is an open virtual interface (GetTangentPlane / IsPointInside). On the GPU the
+// set is closed: a ConvexObj here is anything that can describe itself as an rqcd_obstacle record.
+class ConvexObj {
+ public:
+  virtual ~ConvexObj() {}
+  virtual rqcd_obstacle Record() const = 0;
+};
+
+class Sphere : public ConvexObj {  // Sphere.hpp:40-72
+ public:
+  Sphere(Vec3 center, double radius) : c_(center), r_(radius) {}
+  rqcd_obstacle Record() const override {
+    rqcd_obstacle o = {};
+    o.type = RQCD_SPHERE;
+    o.center[0] = c_.x, o.center[1] = c_.y, o.center[2] = c_.z;
+    o.radius = r_;
+    o.quat[0] = 1;
+    return o;
+  }
+
+ private:
+  Vec3 c_;
+  double r_;
+};
+
+class RectPrism : public ConvexObj {  // RectPrism.hpp:46-123
+ public:
+  RectPrism(Vec3 center, Vec3 sideLengths, Rotation rotation) : c_(center), s_(sideLengths), q_(rotation) {}
+  void SetCenterPoint(Vec3 c) { c_ = c; }
+  void SetSideLengths(Vec3 s) { s_ = s; }
+  void SetRotation(Rotation r) { q_ = r; }
+  rqcd_obstacle Record() const override {
+    rqcd_obstacle o = {};
+    o.type = RQCD_RECT_PRISM;
+    o.center[0] = c_.x, o.center[1] = c_.y, o.center[2] = c_.z;
+    o.side[0] = s_.x, o.side[1] = s_.y, o.side[2] = s_.z;
+    for (int i = 0; i < 4; i++) o.quat[i] = q_.v[i];
+    return o;
+  }
+
+ private:
+  Vec3 c_, s_;
+  Rotation q_;
+};
+
+// A non-rotating obstacle translating along its own quintic: the composition
+// CollisionChecker(traj - obstacleTraj).CollisionCheck(shape, minT) of Trajectory.hpp:121-128.
+class Trajectory;
+class MovingObj : public ConvexObj {
+ public:
+  MovingObj(std::shared_ptr<ConvexObj> shapeAtOrigin, const Trajectory& motion);
+  rqcd_obstacle Record() const override { return rec_; }
+
+ private:
+  rqcd_obstacle rec_;
+};
+
+// Quintic coefficients (index 0 <-> t^5) and the time window; Trajectory.hpp:44-69.
+class Trajectory {
+ public:
+  Trajectory(Vec3 c0, Vec3 c1, Vec3 c2, Vec3 c3, Vec3 c4, Vec3 c5, double startTime, double endTime)
+      : c_{c0, c1, c2, c3, c4, c5}, t0_(startTime), t1_(endTime) {}
+  Vec3 operator[](int i) const { return c_[i]; }
+  double GetStartTime() const { return t0_; }
+  double GetEndTime() const { return t1_; }
+
+ private:
+  Vec3 c_[6];
+  double t0_, t1_;
+};
+
+inline MovingObj::MovingObj(std::shared_ptr<ConvexObj> shape, const Trajectory& motion) : rec_(shape->Record()) {
+  rec_.moving = 1;
+  for (int k = 0; k < 6; k++)
+    for (int d = 0; d < 3; d++) rec_.motion[3 * k + d] = motion[k][d];
+  rec_.motion_t_start = motion.GetStartTime();
+  rec_.motion_t_end = motion.GetEndTime();
+}
+
+}  // namespace CommonMath
+
+namespace rqcd {
+
+// N candidates x M obstacles: the batched call. Boundary conditions are structure-of-arrays (rqcd_bc_soa).
+class Batch {
+ public:
+  explicit Batch(Context& ctx) : ctx_(ctx) {}
+
+  void SetObstacles(const std::vector<std::shared_ptr<CommonMath::ConvexObj>>& obstacles) {
+    std::vector<rqcd_obstacle> rec;
+    for (auto& o : obstacles) rec.push_back(o->Record());
+    ctx_.check(rqcd_set_obstacles(ctx_.get(), rec.data(), (int32_t)rec.size()));
+    m_ = (int32_t)rec.size();
+  }
+
+  struct Result {
+    std::vector<uint8_t> verdict;         // CollisionChecker::CollisionResult per candidate (first hit in index order)
+    std::vector<int32_t> first_obstacle;  // -1 when collision free
+    std::vector<double> cost;             // RapidTrajectoryGenerator::GetCost()
+    rqcd_summary summary;
+  };
+
+  // bc: RQCD_BC_ROWS x n, row r at bc + r*n (host memory). earlyExit = ForestPerformanceEval's inner break.
+  Result GenerateAndCheck(const double* bc, int64_t n, double minTimeSection, uint32_t goalMask = RQCD_GOAL_ALL,
+                          bool earlyExit = false, int64_t indexBase = 0) {
+    Result r;
+    r.verdict.resize(n);
+    r.first_obstacle.resize(n);
+    r.cost.resize(n);
+    rqcd_bc_soa in = {bc, n, goalMask, 0};
+    rqcd_out out = {};
+    out.verdict = r.verdict.data();
+    out.first_obstacle = r.first_obstacle.data();
+    out.cost = r.cost.data();
+    out.summary = &r.summary;
+    ctx_.check(rqcd_generate_check(ctx_.get(), &in, n, minTimeSection, earlyExit ? RQCD_F_EARLY_EXIT : 0, indexBase, &out),
+               true);
+    return r;
+  }
+
+  // PerformanceEval shape: candidate i against its own sphere i (spheres: 4 rows cx, cy, cz, r).
+  Result GenerateAndCheckPairwise(const double* bc, const double* spheres, int64_t n, double minTimeSection,
+                                  uint32_t goalMask = RQCD_GOAL_ALL) {
+    Result r;
+    r.verdict.resize(n);
+    r.cost.resize(n);
+    rqcd_bc_soa in = {bc, n, goalMask, 0};
+    rqcd_out out = {};
+    out.verdict = r.verdict.data();
+    out.cost = r.cost.data();
+    out.summary = &r.summary;
+    ctx_.check(rqcd_generate_check_pairwise(ctx_.get(), &in, spheres, n, n, minTimeSection, 0, 0, &out), true);
+    return r;
+  }
+
+  int32_t NumObstacles() const { return m_; }
+
+ private:
+  Context& ctx_;
+  int32_t m_ = 0;
+};
+
+}  // namespace rqcd
+
+namespace RapidQuadrocopterTrajectoryGenerator {
+
+class RapidTrajectoryGenerator {
+ public:
+  RapidTrajectoryGenerator(const CommonMath::Vec3 x0, const CommonMath::Vec3 v0, const CommonMath::Vec3 a0,
+                           const CommonMath::Vec3 gravity)
+      : grav_(gravity) {
+    for (int i = 0; i < 3; i++) bc_[RQCD_BC_P0 + i] = x0[i], bc_[RQCD_BC_V0 + i] = v0[i], bc_[RQCD_BC_A0 + i] = a0[i];
+    Reset();
+  }
+  void SetGoalPosition(const CommonMath::Vec3 in) { for (unsigned i = 0; i < 3; i++) SetGoalPositionInAxis(i, in[i]); }
+  void SetGoalVelocity(const CommonMath::Vec3 in) { for (unsigned i = 0; i < 3; i++) SetGoalVelocityInAxis(i, in[i]); }
+  void SetGoalAcceleration(const CommonMath::Vec3 in) { for (unsigned i = 0; i < 3; i++) SetGoalAccelerationInAxis(i, in[i]); }
+  void SetGoalPositionInAxis(const unsigned ax, const double in) { mask_ |= RQCD_GOAL_POS(ax), bc_[RQCD_BC_PF + ax] = in; }
+  void SetGoalVelocityInAxis(const unsigned ax, const double in) { mask_ |= RQCD_GOAL_VEL(ax), bc_[RQCD_BC_VF + ax] = in; }
+  void SetGoalAccelerationInAxis(const unsigned ax, const double in) { mask_ |= RQCD_GOAL_ACC(ax), bc_[RQCD_BC_AF + ax] = in; }
+  //! Clears the end-state constraints (goal flags persist across Generate calls, as in the reference).
+  void Reset() {
+    mask_ = 0;
+    for (int i = RQCD_BC_PF; i < RQCD_BC_TF; i++) bc_[i] = 0;
+    cost_ = std::numeric_limits<double>::quiet_NaN();
+    for (double& c : coeffs_) c = std::numeric_limits<double>::quiet_NaN();
+  }
+  //! One rqcd_generate launch with n = 1.
+  void Generate(const double timeToGo) {
+    bc_[RQCD_BC_TF] = timeToGo;
+    rqcd_bc_soa in = {bc_, 1, mask_, 0};
+    rqcd_out out = {};
+    out.cost = &cost_;
+    out.coeffs = coeffs_;
+    out.coeff_stride = 1;
+    rqcd::Context& c = rqcd::Context::Default();
+    c.check(rqcd_generate(c.get(), &in, 1, 0, &out));
+  }
+  double GetCost() const { return cost_; }
+  CommonMath::Trajectory GetTrajectory() const {
+    using CommonMath::Vec3;
+    const double* k = coeffs_;
+    return CommonMath::Trajectory(Vec3(k[0], k[1], k[2]), Vec3(k[3], k[4], k[5]), Vec3(k[6], k[7], k[8]),
+                                  Vec3(k[9], k[10], k[11]), Vec3(k[12], k[13], k[14]), Vec3(k[15], k[16], k[17]), 0,
+                                  bc_[RQCD_BC_TF]);
+  }
+  // alpha, beta, gamma follow from the coefficients the GPU returned (c5 = alpha/120, c4 = beta/24, c3 = gamma/6)
+  // only up to rounding, so they are not offered; use GetTrajectory().
+
+ private:
+  double bc_[RQCD_BC_ROWS] = {0};
+  uint32_t mask_ = 0;
+  double cost_;
+  double coeffs_[RQCD_COEFF_ROWS];
+  CommonMath::Vec3 grav_;
+};
+
+}  // namespace RapidQuadrocopterTrajectoryGenerator
+
+namespace RapidCollisionChecker {
+
+class CollisionChecker {
+ public:
+  enum CollisionResult { NoCollision = 0, Collision = 1, CollisionIndeterminable = 2 };
+
+  explicit CollisionChecker(CommonMath::Trajectory traj) : traj_(traj) {}
+
+  //! One rqcd_set_obstacles + rqcd_check launch with n = 1, m = 1 on the default context.
+  CollisionResult CollisionCheck(std::shared_ptr<CommonMath::ConvexObj> obstacle, double minTimeSection) {
+    rqcd::Context& c = rqcd::Context::Default();
+    rqcd_obstacle rec = obstacle->Record();
+    c.check(rqcd_set_obstacles(c.get(), &rec, 1));
+    double k[RQCD_COEFF_ROWS];
+    for (int i = 0; i < 6; i++)
+      for (int d = 0; d < 3; d++) k[3 * i + d] = traj_[i][d];
+    const double t0 = traj_.GetStartTime(), t1 = traj_.GetEndTime();
+    rqcd_coeff_soa in = {k, 1, &t0, &t1};
+    uint8_t verdict = 0;
+    rqcd_out out = {};
+    out.verdict = &verdict;
+    c.check(rqcd_check(c.get(), &in, nullptr, 1, minTimeSection, 0, 0, &out));
+    return (CollisionResult)verdict;
+  }
+
+  static const char* GetCollisionResultName(CollisionResult fr) {
+    switch (fr) {
+      case NoCollision: return "No Collision";
+      case Collision: return "Collision";
+      case CollisionIndeterminable: return "Collision Indeterminable";
+    }
+    return "Unknown!";
+  }
+
+ private:
+  CommonMath::Trajectory traj_;
+};
+
+}  // namespace RapidCollisionChecker
