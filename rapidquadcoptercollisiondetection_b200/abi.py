@@ -11,7 +11,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "librqcd.so")
+LIB_PATH = os.environ.get("RQCD_LIB") or os.path.join(PKG_DIR, "librqcd.so")  # RQCD_LIB: kernel-variant experiments
 
 # rqcd_status
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_DEPTH_CAP, ERR_NOMEM, ERR_UNSUPPORTED = range(7)

@@ -421,7 +421,10 @@ int rqcd_set_obstacles(rqcd_ctx* ctx, const rqcd_obstacle* obstacles, int32_t m)
     F(OF_CZ) = o.center[2];
     int flags = 0;
     if (o.type == RQCD_SPHERE) {
-      F(OF_H0) = o.radius;
+      // stored as a degenerate prism (identity rotations, zero half sides) + radius: see frame()
+      F(OF_RADIUS) = o.radius;
+      F(OF_R + 0) = F(OF_R + 4) = F(OF_R + 8) = 1.0;
+      F(OF_RI + 0) = F(OF_RI + 4) = F(OF_RI + 8) = 1.0;
     } else {
       flags |= OBS_PRISM;
       for (int i = 0; i < 3; i++) F(OF_H0 + i) = o.side[i] / 2;  // RectPrism.hpp:72-75, :97-99

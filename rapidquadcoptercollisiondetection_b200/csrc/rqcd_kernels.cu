@@ -24,6 +24,9 @@ namespace rqcd {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef RQCD_LOCKSTEP
+#define RQCD_LOCKSTEP 1
+#endif
 
 // ---- TMA bulk copy global -> shared (1-D), completion on an mbarrier ---------------------------------
 RQCD_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -52,6 +55,8 @@ RQCD_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+
+enum SlotRow { SLOT_T0 = 0, SLOT_T1, SLOT_COST, SLOT_X0, SLOT_X1 = SLOT_X0 + 3, kSlotRows = SLOT_X1 + 3 };  // per-thread smem
 
 RQCD_DEV bool better(double ca, long long ia, double cb, long long ib) {
   // candidate a beats b: lower cost, or equal cost and lower index; an empty slot has index -1
@@ -91,7 +96,7 @@ RQCD_DEV void load_trajectory(const CheckParams& p, long long i, double (&c)[18]
 }
 
 template <int MODE, bool MOVING, bool PAIRWISE>
-__global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
+__global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const CheckParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kWarps = kThreads / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -102,8 +107,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
   unsigned long long* wcnt = reinterpret_cast<unsigned long long*>(oflags + mp);  // [kWarps][8]
   double* bcost = reinterpret_cast<double*>(wcnt + kWarps * 8);                   // [kThreads]
   long long* bidx = reinterpret_cast<long long*>(bcost + kThreads);               // [kThreads]
-  double* base = reinterpret_cast<double*>(bidx + kThreads);                      // MOVING: [18][kThreads]
+  double* slot = reinterpret_cast<double*>(bidx + kThreads);                      // [kSlotRows][kThreads], see SlotRow
+  double* base = slot + kSlotRows * kThreads;                                     // MOVING: [18][kThreads]
   __shared__ __align__(8) uint64_t mbar;
+#define RQCD_SLOT(row) slot[(row) * kThreads + tid]
 
   const uint32_t blob_bytes = (uint32_t)(((size_t)p.nfields * mp) * 8 + (size_t)mp * 4);
   if (tid == 0) mbar_init(&mbar, 1);
@@ -116,23 +123,36 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
     mbar_wait(&mbar, 0);
   }
 
-  // ---- lane state
+  // ---- lane state: the trajectory (coefficients in registers for its whole life), the current pair's
+  // interval [ts, tf] with the positions at its ends, and the stack of parked low children
   bool have = false, in_pair = false, exhausted = false, first_frame = false;
   long long idx = 0;
   double c[18];
-  double t0 = 0, t1 = 0, cost = 0, ts = 0, tf = 0;
+#pragma unroll
+  for (int j = 0; j < 18; j++) c[j] = 0.0;
+  double ts = 0, tf = 0;
+  V3 Xs = v3(0, 0, 0), Xf = v3(0, 0, 0);
   int k = 0, verdict = 0, first = -1, sp = 0;
-  double2 stack[kMaxDepth];
+  double2 stack[kMaxDepth][4];  // {ts, lo_tf}, {Xs.x, Xs.y}, {Xs.z, lo_x.x}, {lo_x.y, lo_x.z}
   LaneSphere sph;
   sph.cx = sph.cy = sph.cz = sph.r = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   for (;;) {
+#if RQCD_LOCKSTEP
+    // ---- CTA barrier once per trip: the warps of a CTA walk the (larger than the 32 KB instruction cache) loop
+    // body in step, so an instruction line fetched from L2 serves all of them; the same instruction counts the
+    // CTA's idle lanes for the work-queue trigger
+    const int n_have = __syncthreads_count(have);
+    const bool fetch_now = (kThreads - n_have >= p.refill_min * (kThreads / 32)) || n_have == 0;
+#else
+    const bool fetch_now = true;
+#endif
     // ---- work queue: idle lanes take new candidates
     const unsigned need = __ballot_sync(kFull, !have);
-    if (need != 0 && !exhausted) {
+    if (need != 0 && !exhausted && fetch_now) {
       const int cnt = __popc(need);
-      if (cnt >= p.refill_min || need == kFull) {
+      if (RQCD_LOCKSTEP || cnt >= p.refill_min || need == kFull) {
         unsigned long long b = 0;
         if (lane == 0) b = atomicAdd(p.work_counter, (unsigned long long)cnt);
         b = __shfl_sync(kFull, b, 0);
@@ -141,6 +161,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
           const long long i = (long long)b + __popc(need & lt_mask);
           if (i < p.n) {
             idx = i;
+            double t0, t1, cost;
             load_trajectory<MODE>(p, i, c, t0, t1, cost);
             if (MODE == MODE_BC) {
               if (p.cost) p.cost[i] = cost;
@@ -149,9 +170,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
                 for (int j = 0; j < 18; j++) p.coeffs[j * p.coeff_stride + i] = c[j];
               }
             }
+            RQCD_SLOT(SLOT_T0) = t0;
+            RQCD_SLOT(SLOT_T1) = t1;
+            RQCD_SLOT(SLOT_COST) = cost;
             if (MOVING) {
 #pragma unroll
               for (int j = 0; j < 18; j++) base[j * kThreads + tid] = c[j];
+            } else {
+              // X(t_start), X(t_end) of the trajectory: the same for every obstacle, evaluated once
+              const V3 a = traj_value(c, t0), e = traj_value(c, t1);
+              RQCD_SLOT(SLOT_X0 + 0) = a.x, RQCD_SLOT(SLOT_X0 + 1) = a.y, RQCD_SLOT(SLOT_X0 + 2) = a.z;
+              RQCD_SLOT(SLOT_X1 + 0) = e.x, RQCD_SLOT(SLOT_X1 + 1) = e.y, RQCD_SLOT(SLOT_X1 + 2) = e.z;
             }
             if (PAIRWISE) {
               sph.cx = p.spheres[i];
@@ -168,15 +197,21 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
         }
       }
     }
+#if RQCD_LOCKSTEP
+    // nothing anywhere in the CTA and the fetch above brought nothing: every warp has seen the queue run dry
+    if (n_have == 0 && __syncthreads_count(have) == 0) break;
+    if (__ballot_sync(kFull, have) == 0) continue;  // this warp is done; keep meeting the CTA at the barrier
+#else
     if (exhausted && __ballot_sync(kFull, have) == 0) break;
+#endif
 
     int pv = -1;  // verdict of the pair that completed in this trip, if any
 
     // ---- CollisionChecker::CollisionCheck entry for the lane's next obstacle (CollisionChecker.cpp:70-80);
     // its end-point tests ride on the first frame below
     if (have && !in_pair && k < m) {
-      ts = t0;
-      tf = t1;
+      ts = RQCD_SLOT(SLOT_T0);
+      tf = RQCD_SLOT(SLOT_T1);
       in_pair = true;
       first_frame = true;
       sp = 0;
@@ -187,6 +222,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
 #pragma unroll
           for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid] - tab[(OF_MOTION + j) * mp + k];
           const double ms = tab[OF_MT0 * mp + k], me = tab[OF_MT1 * mp + k];
+          const double t0 = ts, t1 = tf;
           ts = (t0 < ms) ? ms : t0;  // std::max(_startTime, rhs start)
           tf = (me < t1) ? me : t1;  // std::min(_endTime, rhs end)
           if (!(ts <= tf)) {  // no common time (the reference would assert, Trajectory.hpp:68): nothing to hit
@@ -197,6 +233,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
 #pragma unroll
           for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid];
         }
+        Xs = traj_value(c, ts);
+        Xf = traj_value(c, tf);
+      } else {
+        Xs = v3(RQCD_SLOT(SLOT_X0 + 0), RQCD_SLOT(SLOT_X0 + 1), RQCD_SLOT(SLOT_X0 + 2));
+        Xf = v3(RQCD_SLOT(SLOT_X1 + 0), RQCD_SLOT(SLOT_X1 + 1), RQCD_SLOT(SLOT_X1 + 2));
       }
     }
 
@@ -206,14 +247,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
       Children ch;
       int r;
       if (PAIRWISE) {
-        r = frame(c, ts, tf, first_frame, sph, p.min_t, ch);
+        r = frame(c, ts, tf, Xs, Xf, first_frame, sph, p.min_t, ch);
       } else {
         TableObs o;
         o.tab = tab;
         o.mp = mp;
         o.k = min(k, max(m - 1, 0));
         o.flags = oflags[o.k];
-        r = frame(c, ts, tf, first_frame, o, p.min_t, ch);
+        r = frame(c, ts, tf, Xs, Xf, first_frame, o, p.min_t, ch);
       }
       first_frame = false;
       if (in_pair) {
@@ -221,21 +262,30 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
           if (ch.has_hi) {
             if (ch.has_lo) {  // the parent's low tail call waits until the high subtree is clear
               if (sp < kMaxDepth) {
-                stack[sp++] = make_double2(ts, ch.lo_tf);
+                stack[sp][0] = make_double2(ts, ch.lo_tf);
+                stack[sp][1] = make_double2(Xs.x, Xs.y);
+                stack[sp][2] = make_double2(Xs.z, ch.lo_x.x);
+                stack[sp][3] = make_double2(ch.lo_x.y, ch.lo_x.z);
+                sp++;
               } else {
                 pv = 3;
                 in_pair = false;
               }
             }
             ts = ch.hi_ts;
+            Xs = ch.hi_x;
           } else {
             tf = ch.lo_tf;
+            Xf = ch.lo_x;
           }
         } else if (r == STEP_CLEAR) {
           if (sp > 0) {
-            const double2 e = stack[--sp];
-            ts = e.x;
-            tf = e.y;
+            --sp;
+            const double2 e0 = stack[sp][0], e1 = stack[sp][1], e2 = stack[sp][2], e3 = stack[sp][3];
+            ts = e0.x;
+            tf = e0.y;
+            Xs = v3(e1.x, e1.y, e2.x);
+            Xf = v3(e2.y, e3.x, e3.y);
           } else {
             pv = 0;
             in_pair = false;
@@ -278,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
     if (fin) {
       if (p.verdict) p.verdict[idx] = (uint8_t)verdict;
       if (p.first_obstacle) p.first_obstacle[idx] = first;
+      const double cost = RQCD_SLOT(SLOT_COST);
       if (verdict == 0 && cost < bcost[tid]) {  // indices handed to one lane ascend, so ties keep the lowest
         bcost[tid] = cost;
         bidx[tid] = p.index_base + idx;
@@ -285,6 +336,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_check(const CheckParams p) {
       have = false;
     }
   }
+#undef RQCD_SLOT
 
   // ---- CTA partial
   __syncthreads();
@@ -486,6 +538,7 @@ size_t check_smem_bytes(int mp, int nfields, bool moving) {
   size_t b = (size_t)nfields * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
   b += (kThreads / 32) * 8 * 8;                           // warp counters
   b += (size_t)kThreads * 16;                             // best cost / index per thread
+  b += (size_t)kThreads * 8 * 9;                          // t0, t1, cost, X(t0), X(t1) per thread (SlotRow)
   if (moving) b += (size_t)18 * kThreads * 8;             // the lane's own coefficients
   return b;
 }

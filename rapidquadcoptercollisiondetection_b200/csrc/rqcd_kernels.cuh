@@ -6,7 +6,13 @@
 
 namespace rqcd {
 
-constexpr int kThreads = 256;     // threads per CTA of the check kernel
+#ifndef RQCD_THREADS
+#define RQCD_THREADS 256
+#endif
+#ifndef RQCD_MIN_BLOCKS
+#define RQCD_MIN_BLOCKS 2
+#endif
+constexpr int kThreads = RQCD_THREADS;  // threads per CTA of the check kernel
 constexpr int kMaxDepth = 40;     // RQCD_MAX_DEPTH: pending intervals per check
 
 // One CTA's contribution to rqcd_summary; reduced by k_finalize in block order (deterministic).
