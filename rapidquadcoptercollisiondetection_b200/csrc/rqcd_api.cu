@@ -36,6 +36,9 @@ struct DevBuf {
 struct rqcd_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // host-pointer calls: copies overlap the kernel chunk by chunk
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done = nullptr, ev_start = nullptr;
+  long long chunk_override = 0;                              // RQCD_HOST_CHUNK: candidates per chunk (0 = automatic)
   cudaDeviceProp prop;
   // obstacle set
   int m = 0, mp = 0, nfields = OF_STATIC_FIELDS;
@@ -148,13 +151,25 @@ int ensure_partials(rqcd_ctx* ctx, int grid) {
 }
 
 // Everything below `what the caller passed` is device memory here.
+struct RowBlock {  // host rows still to be copied: row r goes to dst + r*n (device), from src + r*src_stride (host)
+  double* dst;
+  const double* src;
+  long long src_stride;
+  int rows;
+};
+
 struct CheckCall {
   int mode = MODE_BC;
   bool pairwise = false;
   CheckParams p = {};
+  RowBlock blocks[5];
+  int nblocks = 0;
+  void add(void* dst, const double* src, long long src_stride, int rows) {
+    blocks[nblocks++] = RowBlock{(double*)dst, src, src_stride, rows};
+  }
 };
 
-int run_check(rqcd_ctx* ctx, CheckCall& cc) {
+int run_check(rqcd_ctx* ctx, CheckCall& cc, bool accumulate = false) {
   const bool moving = !cc.pairwise && ctx->any_moving;
   CheckParams& p = cc.p;
   p.obs_blob = ctx->obs_blob.p;
@@ -175,7 +190,7 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   int st = ensure_partials(ctx, (int)grid);
   if (st != RQCD_OK) return st;
   p.partials = ctx->d_partials;
-  RQCD_CU(launch_check(p, cc.mode, moving, cc.pairwise, (int)grid, ctx->stream, ctx->d_summary));
+  RQCD_CU(launch_check(p, cc.mode, moving, cc.pairwise, (int)grid, ctx->stream, ctx->d_summary, accumulate));
   ctx->launches += 2;  // k_check + k_finalize
   ctx->summary_valid = true;
   return RQCD_OK;
@@ -235,18 +250,6 @@ int stage_outputs(rqcd_ctx* ctx, const rqcd_out* out, long long n, int m, bool w
   return RQCD_OK;
 }
 
-int copy_back(rqcd_ctx* ctx, const rqcd_out* out, long long n, int m, const OutStage& o) {
-  cudaStream_t s = ctx->stream;
-  if (n == 0) return RQCD_OK;
-  if (o.verdict) RQCD_CU(cudaMemcpyAsync(out->verdict, o.verdict, (size_t)n, cudaMemcpyDeviceToHost, s));
-  if (o.first) RQCD_CU(cudaMemcpyAsync(out->first_obstacle, o.first, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-  if (o.matrix && m > 0)
-    RQCD_CU(cudaMemcpyAsync(out->verdict_matrix, o.matrix, (size_t)n * (size_t)m, cudaMemcpyDeviceToHost, s));
-  if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost, o.cost, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
-  if (o.coeffs) RQCD_CU(rows_d2h(out->coeffs, out->coeff_stride, o.coeffs, n, RQCD_COEFF_ROWS, s));
-  return RQCD_OK;
-}
-
 void fill_params_out(CheckParams& p, const OutStage& o) {
   p.verdict = o.verdict;
   p.first_obstacle = o.first;
@@ -263,7 +266,75 @@ int validate_out(const rqcd_out* out, uint32_t flags, long long n) {
   return RQCD_OK;
 }
 
-// Shared tail of the three check entry points once the inputs are on the device.
+// One chunk [c0, c1) of a call whose staged arrays all have row stride n.
+void slice_params(CheckParams& q, const CheckParams& p, long long c0, long long c1, int m) {
+  q = p;
+  q.n = c1 - c0;
+  q.index_base = p.index_base + c0;
+  q.in = p.in + c0;
+  if (p.t_start) q.t_start = p.t_start + c0;
+  if (p.t_end) q.t_end = p.t_end + c0;
+  if (p.cost_in) q.cost_in = p.cost_in + c0;
+  if (p.spheres) q.spheres = p.spheres + c0;
+  if (p.verdict) q.verdict = p.verdict + c0;
+  if (p.first_obstacle) q.first_obstacle = p.first_obstacle + c0;
+  if (p.verdict_matrix) q.verdict_matrix = p.verdict_matrix + c0 * (long long)m;
+  if (p.cost) q.cost = p.cost + c0;
+  if (p.coeffs) q.coeffs = p.coeffs + c0;
+}
+
+// Host-pointer call: the candidate range is cut into chunks; chunk i+1's boundary conditions cross PCIe on the
+// copy stream while chunk i is being checked, and chunk i's verdicts return on a third stream. Per-chunk
+// summaries accumulate on the device in stream order.
+int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long long n, int m, const OutStage& o) {
+  // A chunk must stay several waves of lanes deep (148 SMs x 512 lanes), or the tail of each launch costs more than
+  // the overlap wins: measured on C3, 2^18-candidate chunks beat both 2^17 and one monolithic copy-then-launch.
+  long long chunk = ctx->chunk_override > 0 ? ctx->chunk_override : (n + 3) / 4;
+  if (chunk < (1 << 18) && ctx->chunk_override <= 0) chunk = 1 << 18;
+  chunk = (chunk + 255) / 256 * 256;
+  const CheckParams full = cc.p;
+  cudaStream_t cs = ctx->stream, hs = ctx->h2d_stream, ds = ctx->d2h_stream;
+  RQCD_CU(cudaEventRecord(ctx->ev_start, cs));  // copies must not overtake earlier work queued on the compute stream
+  RQCD_CU(cudaStreamWaitEvent(hs, ctx->ev_start, 0));
+  RQCD_CU(cudaStreamWaitEvent(ds, ctx->ev_start, 0));
+  int ci = 0;
+  for (long long c0 = 0; c0 < n || ci == 0; c0 += chunk, ci++) {
+    const long long c1 = (c0 + chunk < n) ? c0 + chunk : n;
+    const long long w = c1 - c0;
+    if (w > 0) {
+      for (int b = 0; b < cc.nblocks; b++) {
+        const RowBlock& rb = cc.blocks[b];
+        RQCD_CU(cudaMemcpy2DAsync(rb.dst + c0, (size_t)n * 8, rb.src + c0, (size_t)rb.src_stride * 8, (size_t)w * 8,
+                                  rb.rows, cudaMemcpyHostToDevice, hs));
+      }
+    }
+    RQCD_CU(cudaEventRecord(ctx->ev_in[ci & 1], hs));
+    RQCD_CU(cudaStreamWaitEvent(cs, ctx->ev_in[ci & 1], 0));
+    slice_params(cc.p, full, c0, c1, m);
+    int st = run_check(ctx, cc, ci > 0);
+    if (st != RQCD_OK) return st;
+    if (w > 0) {
+      RQCD_CU(cudaEventRecord(ctx->ev_done, cs));
+      RQCD_CU(cudaStreamWaitEvent(ds, ctx->ev_done, 0));
+      if (o.verdict) RQCD_CU(cudaMemcpyAsync(out->verdict + c0, o.verdict + c0, (size_t)w, cudaMemcpyDeviceToHost, ds));
+      if (o.first)
+        RQCD_CU(cudaMemcpyAsync(out->first_obstacle + c0, o.first + c0, (size_t)w * 4, cudaMemcpyDeviceToHost, ds));
+      if (o.matrix && m > 0)
+        RQCD_CU(cudaMemcpyAsync(out->verdict_matrix + c0 * m, o.matrix + c0 * m, (size_t)w * (size_t)m,
+                                cudaMemcpyDeviceToHost, ds));
+      if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost + c0, o.cost + c0, (size_t)w * 8, cudaMemcpyDeviceToHost, ds));
+      if (o.coeffs)
+        RQCD_CU(cudaMemcpy2DAsync(out->coeffs + c0, (size_t)out->coeff_stride * 8, o.coeffs + c0, (size_t)n * 8,
+                                  (size_t)w * 8, RQCD_COEFF_ROWS, cudaMemcpyDeviceToHost, ds));
+    }
+    if (c1 >= n) break;
+  }
+  cc.p = full;
+  RQCD_CU(cudaStreamSynchronize(ds));
+  return RQCD_OK;
+}
+
+// Shared tail of the three check entry points.
 int finish_check(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, uint32_t flags, long long n, int m,
                  bool want_cost_coeffs) {
   OutStage o;
@@ -283,12 +354,8 @@ int finish_check(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, uint32_t fla
   }
   fill_params_out(cc.p, o);
   cc.p.early_exit = (flags & RQCD_F_EARLY_EXIT) ? 1 : 0;
-  int st = run_check(ctx, cc);
+  int st = dev ? run_check(ctx, cc) : run_host_pipeline(ctx, cc, out, n, m, o);
   if (st != RQCD_OK) return st;
-  if (!dev) {
-    st = copy_back(ctx, out, n, m, o);
-    if (st != RQCD_OK) return st;
-  }
   if (out->summary) return fetch_summary(ctx, out->summary);
   if (!dev) RQCD_CU(cudaStreamSynchronize(ctx->stream));
   return RQCD_OK;
@@ -317,6 +384,11 @@ int rqcd_create(rqcd_ctx** out, int device) {
   }
   DeviceGuard g(device);
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counter, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_summary, sizeof(DevSummary));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_summary, sizeof(DevSummary));
@@ -325,6 +397,8 @@ int rqcd_create(rqcd_ctx** out, int device) {
     return RQCD_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  const char* hc = getenv("RQCD_HOST_CHUNK");
+  if (hc && atoll(hc) > 0) ctx->chunk_override = atoll(hc);
   const char* rm = getenv("RQCD_REFILL_MIN");
   if (rm && atoi(rm) >= 1 && atoi(rm) <= 32) ctx->refill_min = atoi(rm);
   *out = ctx;
@@ -344,6 +418,10 @@ void rqcd_destroy(rqcd_ctx* ctx) {
   if (ctx->d_summary) cudaFree(ctx->d_summary);
   if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  for (cudaEvent_t ev : {ctx->ev_in[0], ctx->ev_in[1], ctx->ev_done, ctx->ev_start})
+    if (ev) cudaEventDestroy(ev);
   delete ctx;
 }
 
@@ -506,7 +584,7 @@ int rqcd_generate_check(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, double 
     cc.p.in_stride = in->stride;
   } else {
     RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
-    RQCD_CU(rows_h2d(ctx->s_in.p, in->data, in->stride, n, RQCD_BC_ROWS, ctx->stream));
+    cc.add(ctx->s_in.p, in->data, in->stride, RQCD_BC_ROWS);
     cc.p.in = (const double*)ctx->s_in.p;
     cc.p.in_stride = n;
   }
@@ -535,12 +613,10 @@ int rqcd_check(rqcd_ctx* ctx, const rqcd_coeff_soa* in, const double* cost, int6
     RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_COEFF_ROWS));
     RQCD_CU(ensure(ctx->s_aux, (size_t)n * 8 * 3));
     double* aux = (double*)ctx->s_aux.p;
-    RQCD_CU(rows_h2d(ctx->s_in.p, in->coeffs, in->stride, n, RQCD_COEFF_ROWS, ctx->stream));
-    if (n > 0) {
-      RQCD_CU(cudaMemcpyAsync(aux, in->t_end, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-      if (in->t_start) RQCD_CU(cudaMemcpyAsync(aux + n, in->t_start, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-      if (cost) RQCD_CU(cudaMemcpyAsync(aux + 2 * n, cost, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    }
+    cc.add(ctx->s_in.p, in->coeffs, in->stride, RQCD_COEFF_ROWS);
+    cc.add(aux, in->t_end, n, 1);
+    if (in->t_start) cc.add(aux + n, in->t_start, n, 1);
+    if (cost) cc.add(aux + 2 * n, cost, n, 1);
     cc.p.in = (const double*)ctx->s_in.p;
     cc.p.in_stride = n;
     cc.p.t_end = aux;
@@ -576,8 +652,8 @@ int rqcd_generate_check_pairwise(rqcd_ctx* ctx, const rqcd_bc_soa* in, const dou
   } else {
     RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
     RQCD_CU(ensure(ctx->s_aux, (size_t)n * 8 * 4));
-    RQCD_CU(rows_h2d(ctx->s_in.p, in->data, in->stride, n, RQCD_BC_ROWS, ctx->stream));
-    RQCD_CU(rows_h2d(ctx->s_aux.p, spheres, sphere_stride, n, 4, ctx->stream));
+    cc.add(ctx->s_in.p, in->data, in->stride, RQCD_BC_ROWS);
+    cc.add(ctx->s_aux.p, spheres, sphere_stride, 4);
     cc.p.in = (const double*)ctx->s_in.p;
     cc.p.in_stride = n;
     cc.p.spheres = (const double*)ctx->s_aux.p;
