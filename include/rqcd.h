@@ -209,6 +209,35 @@ int rqcd_generate_check_pairwise(rqcd_ctx* ctx, const rqcd_bc_soa* in, const dou
                                  int64_t sphere_stride, int64_t n, double min_time_section,
                                  uint32_t flags, int64_t index_base, rqcd_out* out);
 
+/* ---- plane boundaries --------------------------------------------------------
+ * CollisionChecker::CollisionCheck(Boundary) (src/CollisionChecker.cpp:25-68; the same test is
+ * RapidTrajectoryGenerator::CheckPositionFeasibility, src/RapidTrajectoryGenerator.cpp:162-212) for every
+ * (trajectory, plane) pair, with the DOCUMENTED intent: Collision (1) when (X(t) - point).normal <= 0 at t_start,
+ * at t_end, or at a time inside the window where the velocity along the normal vanishes; else NoCollision (0).
+ * The reference's own code does not implement that (its solver call overwrites the prepended end times and two
+ * uninitialised slots are read, CollisionChecker.cpp:43-55), so parity for this entry is defined against the
+ * oracle's restatement of the intent, not against the reference binary.
+ * planes: HOST pointer, p records of 6 doubles {point xyz, normal xyz} (Boundary, ConvexObj.hpp:29-53); the normal is
+ * normalised like the reference does (Vec3::GetUnitVector). verdict[n]: 1 if any plane is hit; verdict_matrix[n*p]
+ * row-major per trajectory. Either may be NULL. Host or device pointers per flags. */
+int rqcd_check_planes(rqcd_ctx* ctx, const rqcd_coeff_soa* in, int64_t n, const double* planes, int32_t p,
+                      uint32_t flags, uint8_t* verdict, uint8_t* verdict_matrix);
+int rqcd_generate_check_planes(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const double* planes, int32_t p,
+                               uint32_t flags, uint8_t* verdict, uint8_t* verdict_matrix);
+
+/* ---- input feasibility ---------------------------------------------------------
+ * RapidTrajectoryGenerator::CheckInputFeasibility(fminAllowed, fmaxAllowed, wmaxAllowed, minTimeSection)
+ * (src/RapidTrajectoryGenerator.cpp:74-160) after Generate, per candidate; result[i] is an
+ * rqcd_input_feasibility. gravity: HOST pointer to 3 doubles (the constructor's 4th argument).
+ * group (n int64, may be NULL; host or device per flags): consecutive candidates with equal group[i] are treated as
+ * Generate calls on ONE generator object, which is what ForestPerformanceEval.cpp:177-209 does per batch: the
+ * reference then keeps each axis' acceleration peak times from the first candidate of the group that needed them
+ * (SingleAxisTrajectory.cpp:133-158 caches them and only Reset() clears the cache). NULL = a fresh object per
+ * candidate (PerformanceEval.cpp:140-164). */
+int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const double* gravity, double fmin,
+                           double fmax, double wmax, double min_time_section, const int64_t* group, uint32_t flags,
+                           uint8_t* result);
+
 /* ---- solver unit entry points (test surface of Quartic::solveP3 / solve_quartic,
  * src/quartic.cpp:39-156). coef: 3 (cubic a,b,c) or 4 (quartic a,b,c,d) rows of n doubles, row stride n.
  * roots: 3 or 4 rows of n doubles (row stride n); count[n]. Host or device pointers per flags. */

@@ -229,6 +229,20 @@ class Oracle(_CpuImpl):
         return bc
 
 
+    def check_planes(self, coeffs, t_end, planes, t_start=None):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        planes = np.ascontiguousarray(planes, dtype=np.float64).reshape(-1, 6)
+        n, p = coeffs.shape[1], planes.shape[0]
+        t_end = np.ascontiguousarray(t_end, dtype=np.float64)
+        if t_start is not None:
+            t_start = np.ascontiguousarray(t_start, dtype=np.float64)
+        verdict = np.zeros(n, dtype=np.uint8)
+        matrix = np.zeros((n, max(p, 1)), dtype=np.uint8)
+        inp = abi.CoeffSoa(_ptr(coeffs), n, _ptr(t_start), _ptr(t_end))
+        self._f("check_planes")(C.byref(inp), C.c_int64(n), _ptr(planes), C.c_int32(p), _ptr(verdict), _ptr(matrix))
+        return verdict, matrix
+
+
 class Reference(_CpuImpl):
     """oracle/_ref/libref.so -- the unmodified reference classes behind ref_shim.cpp."""
     prefix = "ref_"

@@ -373,6 +373,53 @@ int orc_check_one(const double coef[18], double t_start, double t_end, const rqc
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * CollisionChecker::CollisionCheck(Boundary) -- src/CollisionChecker.cpp:25-68, DOCUMENTED INTENT.
+ * PARITY UNPINNED against the reference binary: the reference hands `roots` (not roots+2) to the solver, so
+ * the prepended start/end times are overwritten and two uninitialised slots are read (:43-55); NaN roots
+ * reach GetValue and trip its assert. What is restated here is what its comments describe: test the start
+ * time, the end time and every root inside the window.
+ * ---------------------------------------------------------------------------------------------- */
+int orc_check_plane_one(const double coef[18], double t0, double t1, const double plane[6]) {
+  v3 pp = {plane[0], plane[1], plane[2]};
+  v3 pn = v3_unit((v3){plane[3], plane[4], plane[5]}); /* :29 */
+  double c[5] = {0, 0, 0, 0, 0};
+  double nrm[3] = {pn.x, pn.y, pn.z};
+  for (int dim = 0; dim < 3; dim++) {
+    for (int k = 0; k < 5; k++) c[k] += nrm[dim] * ((double)(5 - k) * coef[3 * k + dim]); /* :35-43 */
+  }
+  double roots[6];
+  int rootCount;
+  roots[0] = t0;
+  roots[1] = t1;
+  if (fabs(c[0]) > (double)1e-6) { /* :47-52, writing after the two end times */
+    rootCount = solve_quartic(c[1] / c[0], c[2] / c[0], c[3] / c[0], c[4] / c[0], roots + 2, NULL);
+  } else {
+    rootCount = solve_p3(c[2] / c[1], c[3] / c[1], c[4] / c[1], roots + 2, NULL);
+  }
+  for (int i = 0; i < rootCount + 2; i++) { /* :54-66 */
+    if (!(roots[i] >= t0 && roots[i] <= t1)) continue; /* outside the domain, or NaN */
+    if (v3_dot(v3_sub(traj_value(coef, roots[i]), pp), pn) <= 0) return RQCD_COLLISION;
+  }
+  return RQCD_NO_COLLISION;
+}
+
+void orc_check_planes(const rqcd_coeff_soa* in, int64_t n, const double* planes, int32_t p, uint8_t* verdict,
+                      uint8_t* matrix) {
+  for (int64_t i = 0; i < n; i++) {
+    double coef[18];
+    for (int k = 0; k < 18; k++) coef[k] = in->coeffs[k * in->stride + i];
+    double t0 = in->t_start ? in->t_start[i] : 0.0, t1 = in->t_end[i];
+    int any = 0;
+    for (int32_t k = 0; k < p; k++) {
+      int v = orc_check_plane_one(coef, t0, t1, planes + 6 * k);
+      if (matrix) matrix[i * p + k] = (uint8_t)v;
+      any |= v;
+    }
+    if (verdict) verdict[i] = (uint8_t)any;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * SingleAxisTrajectory::GenerateTrajectory -- src/SingleAxisTrajectory.cpp:57-120
  * ---------------------------------------------------------------------------------------------- */
 typedef struct axis_t {

@@ -6,7 +6,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load it; the product library (librqcd.so) never links or calls it.
  *
- * Parity status: PINNED.  oracle.c is checked (tests/test_oracle_*.py) against
+ * Parity status: PINNED (one exception: orc_check_planes, see below).  oracle.c is checked (tests/test_oracle_*.py) against
  *  - the reference's checked-in known answers (data/PerformanceEval.txt:23-25,
  *    data/ForestPerfEval.txt:28-29, data/ForestPerfEval.csv, data/ForestPerfEvaltreeParamsCSV.csv), and
  *  - oracle/_ref/libref.so, the UNMODIFIED reference sources compiled where they lie
@@ -56,6 +56,12 @@ void orc_check(const rqcd_coeff_soa* in, const double* cost, int64_t n, const rq
 void orc_generate_check_pairwise(const rqcd_bc_soa* in, const double* spheres, int64_t sphere_stride,
                                  int64_t n, double min_time_section, int64_t index_base, rqcd_out* out,
                                  int nthreads, orc_stats* stats);
+
+/* CollisionChecker::CollisionCheck(Boundary) (src/CollisionChecker.cpp:25-68), the documented intent; parity
+ * UNPINNED against the reference binary (its code reads uninitialised memory there, see oracle.c). */
+int orc_check_plane_one(const double coef[18], double t0, double t1, const double plane[6]);
+void orc_check_planes(const rqcd_coeff_soa* in, int64_t n, const double* planes, int32_t p, uint8_t* verdict,
+                      uint8_t* matrix);
 
 /* RapidTrajectoryGenerator::CheckInputFeasibility (src/RapidTrajectoryGenerator.cpp:74-160).
  * group (or NULL): consecutive trajectories with equal group[i] are checked with ONE generator object,

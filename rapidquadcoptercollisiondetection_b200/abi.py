@@ -113,6 +113,12 @@ SYMBOLS = {
         C.c_int,
         [_VP, C.POINTER(BcSoa), _VP, C.c_int64, C.c_int64, C.c_double, C.c_uint32, C.c_int64, C.POINTER(Out)],
     ),
+    "rqcd_check_planes": (C.c_int, [_VP, C.POINTER(CoeffSoa), C.c_int64, _VP, C.c_int32, C.c_uint32, _VP, _VP]),
+    "rqcd_generate_check_planes": (C.c_int, [_VP, C.POINTER(BcSoa), C.c_int64, _VP, C.c_int32, C.c_uint32, _VP, _VP]),
+    "rqcd_check_input_feasibility": (
+        C.c_int,
+        [_VP, C.POINTER(BcSoa), C.c_int64, _VP, C.c_double, C.c_double, C.c_double, C.c_double, _VP, C.c_uint32, _VP],
+    ),
     "rqcd_solve_cubic": (C.c_int, [_VP, _VP, C.c_int64, C.c_uint32, _VP, _VP]),
     "rqcd_solve_quartic": (C.c_int, [_VP, _VP, C.c_int64, C.c_uint32, _VP, _VP]),
     "rqcd_merge_summaries": (C.c_int, [C.POINTER(Summary), C.c_int32, C.POINTER(Summary)]),

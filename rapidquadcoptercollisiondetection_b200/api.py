@@ -164,6 +164,43 @@ class Context:
         res["status"] = st
         return res
 
+    def check_planes(self, coeffs, t_end, planes, t_start=None):
+        """planes: (p, 6) array of {point, normal}. Returns verdict (n,), verdict_matrix (n, p)."""
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        planes = np.ascontiguousarray(planes, dtype=np.float64).reshape(-1, 6)
+        n, p = coeffs.shape[1], planes.shape[0]
+        t_end = np.ascontiguousarray(t_end, dtype=np.float64)
+        if t_start is not None:
+            t_start = np.ascontiguousarray(t_start, dtype=np.float64)
+        verdict = np.full(n, 255, dtype=np.uint8)
+        matrix = np.full((n, max(p, 1)), 255, dtype=np.uint8)
+        inp = abi.CoeffSoa(_ptr(coeffs), n, _ptr(t_start), _ptr(t_end))
+        self._chk(self.lib.rqcd_check_planes(self.h, C.byref(inp), n, _ptr(planes), p, 0, _ptr(verdict), _ptr(matrix)))
+        return verdict, matrix
+
+    def generate_check_planes(self, bc, planes, goal_mask=abi.GOAL_ALL):
+        bc = np.ascontiguousarray(bc, dtype=np.float64)
+        planes = np.ascontiguousarray(planes, dtype=np.float64).reshape(-1, 6)
+        n, p = bc.shape[1], planes.shape[0]
+        verdict = np.full(n, 255, dtype=np.uint8)
+        matrix = np.full((n, max(p, 1)), 255, dtype=np.uint8)
+        inp = abi.BcSoa(_ptr(bc), n, goal_mask, 0)
+        self._chk(self.lib.rqcd_generate_check_planes(self.h, C.byref(inp), n, _ptr(planes), p, 0, _ptr(verdict), _ptr(matrix)))
+        return verdict, matrix
+
+    def input_feasibility(self, bc, goal_mask=abi.GOAL_ALL, gravity=(0.0, 0.0, -9.81), fmin=5.0, fmax=30.0, wmax=20.0,
+                          min_t=0.002, group=None):
+        bc = np.ascontiguousarray(bc, dtype=np.float64)
+        n = bc.shape[1]
+        g = np.asarray(gravity, dtype=np.float64)
+        if group is not None:
+            group = np.ascontiguousarray(group, dtype=np.int64)
+        res = np.full(n, 255, dtype=np.uint8)
+        inp = abi.BcSoa(_ptr(bc), n, goal_mask, 0)
+        self._chk(self.lib.rqcd_check_input_feasibility(self.h, C.byref(inp), n, _ptr(g), fmin, fmax, wmax, min_t, _ptr(group), 0,
+                                                  _ptr(res)))
+        return res
+
     def solve_cubic(self, coef):
         coef = np.ascontiguousarray(coef, dtype=np.float64)
         n = coef.shape[1]

@@ -52,7 +52,7 @@ struct rqcd_ctx {
   DevSummary* h_summary = nullptr;  // pinned
   bool summary_valid = false;
   // staging for host-pointer calls
-  DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count;
+  DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group;
   int refill_min = 4;
   unsigned long long launches = 0;
   char last_error[512] = {0};
@@ -410,8 +410,8 @@ void rqcd_destroy(rqcd_ctx* ctx) {
   DeviceGuard g(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   release(ctx->obs_blob);
-  DevBuf* bufs[] = {&ctx->s_in,   &ctx->s_aux,    &ctx->s_verdict, &ctx->s_first, &ctx->s_matrix,
-                    &ctx->s_cost, &ctx->s_coeffs, &ctx->s_roots,   &ctx->s_count};
+  DevBuf* bufs[] = {&ctx->s_in,     &ctx->s_aux,   &ctx->s_verdict, &ctx->s_first,  &ctx->s_matrix, &ctx->s_cost,
+                    &ctx->s_coeffs, &ctx->s_roots, &ctx->s_count,   &ctx->s_planes, &ctx->s_peaks,  &ctx->s_group};
   for (DevBuf* b : bufs) release(*b);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
@@ -660,6 +660,138 @@ int rqcd_generate_check_pairwise(rqcd_ctx* ctx, const rqcd_bc_soa* in, const dou
     cc.p.sphere_stride = n;
   }
   return finish_check(ctx, cc, out, flags & ~RQCD_F_EARLY_EXIT, n, 1, true);
+}
+
+static int planes_common(rqcd_ctx* ctx, int mode, CheckParams& p, RowBlock* blocks, int nblocks, int64_t n,
+                         const double* planes, int32_t np, uint32_t flags, uint8_t* verdict, uint8_t* matrix) {
+  if (np < 0 || (np > 0 && !planes)) return RQCD_ERR_INVALID_ARG;
+  // Boundary.normal = normal.GetUnitVector() (CollisionChecker.cpp:29): float-narrowed norm, Vec3.hpp:117-120
+  std::vector<double> prep((size_t)(np > 0 ? np : 1) * 6);
+  for (int k = 0; k < np; k++) {
+    const double* q = planes + 6 * k;
+    for (int i = 0; i < 6; i++)
+      if (!std::isfinite(q[i])) return RQCD_ERR_INVALID_ARG;
+    const double nn = (double)(float)std::sqrt(q[3] * q[3] + q[4] * q[4] + q[5] * q[5]);
+    for (int i = 0; i < 3; i++) {
+      prep[6 * k + i] = q[i];
+      prep[6 * k + 3 + i] = q[3 + i] / nn;
+    }
+  }
+  RQCD_CU(ensure(ctx->s_planes, prep.size() * 8));
+  RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  RQCD_CU(cudaMemcpy(ctx->s_planes.p, prep.data(), prep.size() * 8, cudaMemcpyHostToDevice));
+  if (n == 0) return RQCD_OK;
+  const bool dev = flags & RQCD_F_DEVICE_PTRS;
+  uint8_t *dv = verdict, *dm = matrix;
+  if (!dev) {
+    for (int b = 0; b < nblocks; b++)
+      RQCD_CU(rows_h2d(blocks[b].dst, blocks[b].src, blocks[b].src_stride, n, blocks[b].rows, ctx->stream));
+    if (verdict) {
+      RQCD_CU(ensure(ctx->s_verdict, (size_t)n));
+      dv = (uint8_t*)ctx->s_verdict.p;
+    }
+    if (matrix) {
+      RQCD_CU(ensure(ctx->s_matrix, (size_t)n * (size_t)(np > 0 ? np : 1)));
+      dm = (uint8_t*)ctx->s_matrix.p;
+    }
+  }
+  p.n = n;
+  RQCD_CU(launch_planes(p, mode, (const double*)ctx->s_planes.p, np, dv, dm, ctx->stream));
+  ctx->launches++;
+  if (!dev) {
+    if (verdict) RQCD_CU(cudaMemcpyAsync(verdict, dv, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (matrix && np > 0) RQCD_CU(cudaMemcpyAsync(matrix, dm, (size_t)n * np, cudaMemcpyDeviceToHost, ctx->stream));
+    RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return RQCD_OK;
+}
+
+int rqcd_check_planes(rqcd_ctx* ctx, const rqcd_coeff_soa* in, int64_t n, const double* planes, int32_t np,
+                      uint32_t flags, uint8_t* verdict, uint8_t* matrix) {
+  if (!ctx || !in || n < 0 || (n > 0 && (!in->coeffs || !in->t_end)) || in->stride < n) return RQCD_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  CheckParams p = {};
+  RowBlock blocks[3];
+  int nb = 0;
+  if (flags & RQCD_F_DEVICE_PTRS) {
+    p.in = in->coeffs;
+    p.in_stride = in->stride;
+    p.t_start = in->t_start;
+    p.t_end = in->t_end;
+  } else {
+    RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_COEFF_ROWS));
+    RQCD_CU(ensure(ctx->s_aux, (size_t)n * 8 * 2));
+    double* aux = (double*)ctx->s_aux.p;
+    blocks[nb++] = RowBlock{(double*)ctx->s_in.p, in->coeffs, in->stride, RQCD_COEFF_ROWS};
+    blocks[nb++] = RowBlock{aux, in->t_end, n, 1};
+    if (in->t_start) blocks[nb++] = RowBlock{aux + n, in->t_start, n, 1};
+    p.in = (const double*)ctx->s_in.p;
+    p.in_stride = n;
+    p.t_end = aux;
+    p.t_start = in->t_start ? aux + n : nullptr;
+  }
+  return planes_common(ctx, MODE_COEFF, p, blocks, nb, n, planes, np, flags, verdict, matrix);
+}
+
+int rqcd_generate_check_planes(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const double* planes, int32_t np,
+                               uint32_t flags, uint8_t* verdict, uint8_t* matrix) {
+  if (!ctx || !in || n < 0 || (n > 0 && !in->data) || in->stride < n) return RQCD_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  CheckParams p = {};
+  p.goal_mask = in->goal_mask;
+  RowBlock blocks[1];
+  int nb = 0;
+  if (flags & RQCD_F_DEVICE_PTRS) {
+    p.in = in->data;
+    p.in_stride = in->stride;
+  } else {
+    RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
+    blocks[nb++] = RowBlock{(double*)ctx->s_in.p, in->data, in->stride, RQCD_BC_ROWS};
+    p.in = (const double*)ctx->s_in.p;
+    p.in_stride = n;
+  }
+  return planes_common(ctx, MODE_BC, p, blocks, nb, n, planes, np, flags, verdict, matrix);
+}
+
+int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const double* gravity, double fmin,
+                           double fmax, double wmax, double min_time_section, const int64_t* group, uint32_t flags,
+                           uint8_t* result) {
+  if (!ctx || !in || !gravity || n < 0 || (n > 0 && (!in->data || !result)) || in->stride < n ||
+      bad_min_t(min_time_section))
+    return RQCD_ERR_INVALID_ARG;
+  if (n == 0) return RQCD_OK;
+  DeviceGuard g(ctx->device);
+  const bool dev = flags & RQCD_F_DEVICE_PTRS;
+  CheckParams p = {};
+  p.goal_mask = in->goal_mask;
+  p.n = n;
+  const long long* dgroup = (const long long*)group;
+  uint8_t* dres = result;
+  if (dev) {
+    p.in = in->data;
+    p.in_stride = in->stride;
+  } else {
+    RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
+    RQCD_CU(rows_h2d(ctx->s_in.p, in->data, in->stride, n, RQCD_BC_ROWS, ctx->stream));
+    p.in = (const double*)ctx->s_in.p;
+    p.in_stride = n;
+    if (group) {
+      RQCD_CU(ensure(ctx->s_group, (size_t)n * 8));
+      RQCD_CU(cudaMemcpyAsync(ctx->s_group.p, group, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+      dgroup = (const long long*)ctx->s_group.p;
+    }
+    RQCD_CU(ensure(ctx->s_verdict, (size_t)n));
+    dres = (uint8_t*)ctx->s_verdict.p;
+  }
+  if (group) RQCD_CU(ensure(ctx->s_peaks, (size_t)n * 8 * 6));
+  RQCD_CU(launch_feasibility(p, gravity, fmin, fmax, wmax, min_time_section, dgroup, (double*)ctx->s_peaks.p, dres,
+                             ctx->stream));
+  ctx->launches += group ? 2 : 1;
+  if (!dev) {
+    RQCD_CU(cudaMemcpyAsync(result, dres, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return RQCD_OK;
 }
 
 static int solve_common(rqcd_ctx* ctx, bool quartic, const double* coef, int64_t n, uint32_t flags, double* roots,

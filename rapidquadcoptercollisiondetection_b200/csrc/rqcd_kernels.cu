@@ -446,6 +446,154 @@ __global__ void __launch_bounds__(256) k_generate(const double* bc, long long st
   }
 }
 
+// ---- CollisionChecker::CollisionCheck(Boundary) (src/CollisionChecker.cpp:25-68), documented intent: the
+// trajectory is on the wrong side of the plane if (X(t) - point).normal <= 0 at t_start, t_end or at any time
+// inside the window where its velocity along the normal vanishes. (The reference prepends the two end times to
+// `roots` but then lets the solver overwrite them and reads two uninitialised slots, :43-55; the end times are
+// tested here and nothing else is.) planes: prepared on the host, 6 doubles each: point, unit normal
+// (Vec3::GetUnitVector's float-narrowed norm, :29).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_planes(const CheckParams p, const double* planes, int np, uint8_t* verdict,
+                                                uint8_t* matrix) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < p.n; i0 += step) {  // warp-uniform
+    const long long i = i0 + (threadIdx.x & 31);
+    const bool live = i < p.n;
+    const long long j = live ? i : p.n - 1;
+    double c[18], t0, t1, cost;
+    load_trajectory<MODE>(p, j, c, t0, t1, cost);
+    const V3 Xs = traj_value(c, t0), Xf = traj_value(c, t1);
+    int first_hit = 0;
+    for (int k = 0; k < np; k++) {
+      const double* q = planes + 6 * k;
+      const V3 pp = v3(q[0], q[1], q[2]), pn = v3(q[3], q[4], q[5]);
+      double r0, r1, r2, r3;
+      const int n = critical_times(c, pn, r0, r1, r2, r3);
+      bool hit = on_obstacle_side(Xs, pp, pn) | on_obstacle_side(Xf, pp, pn);
+#define RQCD_PLANE_ROOT(idx, r) \
+  if (n > idx && r >= t0 && r <= t1) hit = hit | on_obstacle_side(traj_value(c, r), pp, pn);
+      RQCD_PLANE_ROOT(0, r0)
+      RQCD_PLANE_ROOT(1, r1)
+      RQCD_PLANE_ROOT(2, r2)
+      RQCD_PLANE_ROOT(3, r3)
+#undef RQCD_PLANE_ROOT
+      __syncwarp();
+      if (live && matrix) matrix[i * (long long)np + k] = hit ? 1 : 0;
+      if (hit && !first_hit) first_hit = 1;
+    }
+    if (live && verdict) verdict[i] = (uint8_t)first_hit;
+  }
+}
+
+// ---- RapidTrajectoryGenerator::CheckInputFeasibility (src/RapidTrajectoryGenerator.cpp:74-160) --------------------
+RQCD_DEV void feas_axes(const CheckParams& p, long long i, AxisState (&ax)[3], double& Tf) {
+  const double* d = p.in;
+  const long long s = p.in_stride;
+  Tf = d[18 * s + i];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double p0 = d[(0 + k) * s + i], v0 = d[(3 + k) * s + i], a0 = d[(6 + k) * s + i];
+    const AxisParams q = gen_axis(p0, v0, a0, d[(9 + k) * s + i], d[(12 + k) * s + i], d[(15 + k) * s + i],
+                                  (p.goal_mask >> (3 * k)) & 1, (p.goal_mask >> (3 * k + 1)) & 1,
+                                  (p.goal_mask >> (3 * k + 2)) & 1, Tf);
+    ax[k].a0 = a0;
+    ax[k].a = q.a;
+    ax[k].b = q.b;
+    ax[k].g = q.g;
+    acc_peak_times(ax[k], ax[k].pk0, ax[k].pk1);
+  }
+}
+
+struct FeasArgs {
+  double grav[3];
+  double fmin, fmax, wmax, min_t;
+};
+
+// The reference caches each axis' acceleration peak times in the generator object and clears them only in
+// Reset()/SetInitialState() (SingleAxisTrajectory.cpp:133-158): a driver that reuses ONE object for a batch
+// (ForestPerformanceEval.cpp:177-209) evaluates every candidate of the batch with the peak times of the first
+// candidate that reached GetMinMaxAcc on that axis. One thread per group start walks its group in order until all
+// three axes are initialised (normally the first candidate) and writes the group's peak times for every member.
+__global__ void __launch_bounds__(128) k_feas_group_peaks(const CheckParams p, const FeasArgs fa, const long long* group,
+                                                          double* peaks /* 6 rows x n */) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    if (i > 0 && group[i] == group[i - 1]) continue;
+    bool init[3] = {false, false, false};
+    double pk[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    long long j = i;
+    for (; j < p.n && group[j] == group[i]; j++) {
+      if (init[0] && init[1] && init[2]) continue;
+      AxisState ax[3];
+      double Tf;
+      feas_axes(p, j, ax, Tf);
+      double own[3][2];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        own[k][0] = ax[k].pk0;
+        own[k][1] = ax[k].pk1;
+        if (init[k]) {
+          ax[k].pk0 = pk[k][0];
+          ax[k].pk1 = pk[k][1];
+        }
+      }
+      bool reached[3] = {false, false, false};
+      feas_frame(ax, fa.grav, fa.fmin, fa.fmax, fa.wmax, 0.0, Tf, fa.min_t, reached);
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+        if (reached[k] && !init[k]) {
+          init[k] = true;
+          pk[k][0] = own[k][0];
+          pk[k][1] = own[k][1];
+        }
+    }
+    for (long long q = i; q < j; q++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        peaks[(2 * k) * p.n + q] = pk[k][0];
+        peaks[(2 * k + 1) * p.n + q] = pk[k][1];
+      }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_feas(const CheckParams p, const FeasArgs fa, const double* peaks, uint8_t* result) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    AxisState ax[3];
+    double Tf;
+    feas_axes(p, i, ax, Tf);
+    if (peaks) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        ax[k].pk0 = peaks[(2 * k) * p.n + i];
+        ax[k].pk1 = peaks[(2 * k + 1) * p.n + i];
+      }
+    }
+    // the recursion "first half, then (if feasible) second half" as a stack of pending second halves
+    double2 stack[kMaxDepth];
+    int sp = 0, res;
+    double t1 = 0.0, t2 = Tf;
+    for (;;) {
+      bool reached[3];
+      res = feas_frame(ax, fa.grav, fa.fmin, fa.fmax, fa.wmax, t1, t2, fa.min_t, reached);
+      if (res == FEAS_SPLIT) {
+        const double th = (t1 + t2) / 2;
+        if (sp >= kMaxDepth) {
+          res = RQCD_INPUT_INDETERMINABLE_;
+          break;
+        }
+        stack[sp++] = make_double2(th, t2);
+        t2 = th;
+      } else if (res == RQCD_INPUT_FEASIBLE_ && sp > 0) {
+        const double2 e = stack[--sp];
+        t1 = e.x;
+        t2 = e.y;
+      } else {
+        break;
+      }
+    }
+    result[i] = (uint8_t)res;
+  }
+}
+
 // ---- solver unit kernels (test surface of Quartic::solveP3 / solve_quartic) ---------------------------
 __global__ void __launch_bounds__(256) k_solve(bool quartic, const double* coef, long long n, double* roots, int* count) {
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
@@ -585,6 +733,31 @@ cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairw
   e = cudaLaunchKernel(select_check(mode, moving, pairwise), dim3(grid), dim3(kThreads), args, smem, s);
   if (e != cudaSuccess) return e;
   k_finalize<<<1, 256, 0, s>>>(p.partials, grid, d_summary, accumulate ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, int np, uint8_t* verdict, uint8_t* matrix,
+                          cudaStream_t s) {
+  if (p.n <= 0) return cudaSuccess;
+  const int grid = grid_for(p.n, 148 * 8);
+  if (mode == MODE_BC) k_planes<MODE_BC><<<grid, 256, 0, s>>>(p, planes, np, verdict, matrix);
+  else k_planes<MODE_COEFF><<<grid, 256, 0, s>>>(p, planes, np, verdict, matrix);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], double fmin, double fmax, double wmax,
+                               double min_t, const long long* group, double* peaks, uint8_t* result, cudaStream_t s) {
+  if (p.n <= 0) return cudaSuccess;
+  FeasArgs fa;
+  for (int k = 0; k < 3; k++) fa.grav[k] = grav[k];
+  fa.fmin = fmin, fa.fmax = fmax, fa.wmax = wmax, fa.min_t = min_t;
+  const int grid = (int)((p.n + 127) / 128 < 148 * 16 ? (p.n + 127) / 128 : 148 * 16);
+  if (group) {
+    k_feas_group_peaks<<<grid, 128, 0, s>>>(p, fa, group, peaks);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  k_feas<<<grid, 128, 0, s>>>(p, fa, group ? peaks : nullptr, result);
   return cudaGetLastError();
 }
 

@@ -70,6 +70,11 @@ cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairw
 int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, size_t smem);
 cudaError_t check_prepare(int mode, bool moving, bool pairwise, size_t smem);  // opt in to large dynamic smem
 
+cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, int np, uint8_t* verdict, uint8_t* matrix,
+                          cudaStream_t s);
+// group may be null; peaks: scratch of 6*n doubles, needed when group is given
+cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], double fmin, double fmax, double wmax,
+                               double min_t, const long long* group, double* peaks, uint8_t* result, cudaStream_t s);
 cudaError_t launch_generate(const double* bc, long long stride, unsigned goal_mask, long long n, double* cost,
                             double* coeffs, long long coeff_stride, cudaStream_t s);
 cudaError_t launch_solve(bool quartic, const double* coef, long long n, double* roots, int* count, cudaStream_t s);
