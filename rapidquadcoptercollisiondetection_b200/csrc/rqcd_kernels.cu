@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   int n_have = 0;
   unsigned trip = 0;
   for (;;) {
-#if RQCD_LOCKSTEP
+#if RQCD_LOCKSTEP == 1
     // ---- CTA barrier once per trip: the warps of a CTA walk the (larger than the 32 KB instruction cache) loop
     // body in step, so an instruction line fetched from L2 serves all of them; the same instruction counts the
     // CTA's idle lanes for the work-queue trigger
@@ -154,8 +154,9 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
     const bool fetch_now = true;
 #endif
     // ---- work queue: idle lanes take new candidates
+    auto fetch_work = [&]() {
     const unsigned need = __ballot_sync(kFull, !have);
-    if (need != 0 && !exhausted && fetch_now) {
+    if (need != 0 && !exhausted) {
       const int cnt = __popc(need);
       if (RQCD_LOCKSTEP || cnt >= p.refill_min || need == kFull) {
         unsigned long long b = 0;
@@ -202,7 +203,9 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         }
       }
     }
-#if RQCD_LOCKSTEP
+    };
+    if (fetch_now) fetch_work();
+#if RQCD_LOCKSTEP == 1
     // nothing anywhere in the CTA and the fetch above brought nothing: every warp has seen the queue run dry
     if (n_have == 0 && __syncthreads_count(have) == 0) break;
     if (__ballot_sync(kFull, have) == 0) continue;  // this warp is done; keep meeting the CTA at the barrier
@@ -262,43 +265,36 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         r = frame(c, ts, tf, Xs, Xf, first_frame, o, p.min_t, ch);
       }
       first_frame = false;
-      if (in_pair) {
-        if (r == STEP_CHILD) {
-          if (ch.has_hi) {
-            if (ch.has_lo) {  // the parent's low tail call waits until the high subtree is clear
-              if (sp < kMaxDepth) {
-                stack[sp][0] = make_double2(ts, ch.lo_tf);
-                stack[sp][1] = make_double2(Xs.x, Xs.y);
-                stack[sp][2] = make_double2(Xs.z, ch.lo_x.x);
-                stack[sp][3] = make_double2(ch.lo_x.y, ch.lo_x.z);
-                sp++;
-              } else {
-                pv = 3;
-                in_pair = false;
-              }
-            }
-            ts = ch.hi_ts;
-            Xs = ch.hi_x;
-          } else {
-            tf = ch.lo_tf;
-            Xf = ch.lo_x;
-          }
-        } else if (r == STEP_CLEAR) {
-          if (sp > 0) {
-            --sp;
-            const double2 e0 = stack[sp][0], e1 = stack[sp][1], e2 = stack[sp][2], e3 = stack[sp][3];
-            ts = e0.x;
-            tf = e0.y;
-            Xs = v3(e1.x, e1.y, e2.x);
-            Xf = v3(e2.y, e3.x, e3.y);
-          } else {
-            pv = 0;
-            in_pair = false;
-          }
+      // state update, written with selects: one instruction stream for the common cases (no child; one child)
+      const bool child = in_pair & (r == STEP_CHILD);
+      const bool to_hi = child & ch.has_hi, to_lo = child & !ch.has_hi;
+      const bool clear = in_pair & (r == STEP_CLEAR);
+      if (to_hi & ch.has_lo) {  // both children: the parent's low tail call waits until the high subtree is clear
+        if (sp < kMaxDepth) {
+          stack[sp][0] = make_double2(ts, ch.lo_tf);
+          stack[sp][1] = make_double2(Xs.x, Xs.y);
+          stack[sp][2] = make_double2(Xs.z, ch.lo_x.x);
+          stack[sp][3] = make_double2(ch.lo_x.y, ch.lo_x.z);
+          sp++;
         } else {
-          pv = r;
+          pv = 3;
           in_pair = false;
         }
+      }
+      ts = to_hi ? ch.t_next : ts;
+      Xs = v3(to_hi ? ch.x_next.x : Xs.x, to_hi ? ch.x_next.y : Xs.y, to_hi ? ch.x_next.z : Xs.z);
+      tf = to_lo ? ch.t_next : tf;
+      Xf = v3(to_lo ? ch.x_next.x : Xf.x, to_lo ? ch.x_next.y : Xf.y, to_lo ? ch.x_next.z : Xf.z);
+      if (clear & (sp > 0)) {  // subtree clear: resume the innermost parked low child
+        --sp;
+        const double2 e0 = stack[sp][0], e1 = stack[sp][1], e2 = stack[sp][2], e3 = stack[sp][3];
+        ts = e0.x;
+        tf = e0.y;
+        Xs = v3(e1.x, e1.y, e2.x);
+        Xf = v3(e2.y, e3.x, e3.y);
+      } else if (in_pair & !child) {  // NoCollision with nothing parked, Collision or Indeterminable: the pair is done
+        pv = clear ? 0 : r;
+        in_pair = false;
       }
     }
 
