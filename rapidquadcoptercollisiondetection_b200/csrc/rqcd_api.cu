@@ -25,6 +25,7 @@ static_assert(sizeof(DevSummary) == sizeof(rqcd_summary), "DevSummary mirrors rq
 namespace {
 
 constexpr size_t kMaxSmem = 227 * 1024;
+constexpr int kMaxChunks = 64;
 
 struct DevBuf {
   void* p = nullptr;
@@ -50,6 +51,8 @@ struct rqcd_ctx {
   int partial_cap = 0;
   DevSummary* d_summary = nullptr;
   DevSummary* h_summary = nullptr;  // pinned
+  unsigned long long* d_stream = nullptr;  // [0] progress, [1] error flag (streaming host-pointer calls)
+  unsigned long long* h_stream = nullptr;  // pinned: [0..kMaxChunks) cumulative counts, [kMaxChunks] error read-back
   bool summary_valid = false;
   // staging for host-pointer calls
   DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group;
@@ -266,71 +269,59 @@ int validate_out(const rqcd_out* out, uint32_t flags, long long n) {
   return RQCD_OK;
 }
 
-// One chunk [c0, c1) of a call whose staged arrays all have row stride n.
-void slice_params(CheckParams& q, const CheckParams& p, long long c0, long long c1, int m) {
-  q = p;
-  q.n = c1 - c0;
-  q.index_base = p.index_base + c0;
-  q.in = p.in + c0;
-  if (p.t_start) q.t_start = p.t_start + c0;
-  if (p.t_end) q.t_end = p.t_end + c0;
-  if (p.cost_in) q.cost_in = p.cost_in + c0;
-  if (p.spheres) q.spheres = p.spheres + c0;
-  if (p.verdict) q.verdict = p.verdict + c0;
-  if (p.first_obstacle) q.first_obstacle = p.first_obstacle + c0;
-  if (p.verdict_matrix) q.verdict_matrix = p.verdict_matrix + c0 * (long long)m;
-  if (p.cost) q.cost = p.cost + c0;
-  if (p.coeffs) q.coeffs = p.coeffs + c0;
-}
-
-// Host-pointer call: the candidate range is cut into chunks; chunk i+1's boundary conditions cross PCIe on the
-// copy stream while chunk i is being checked, and chunk i's verdicts return on a third stream. Per-chunk
-// summaries accumulate on the device in stream order.
+// Host-pointer call: ONE persistent launch over the whole range that starts as soon as the first chunk of
+// boundary conditions has crossed PCIe. The remaining chunks follow on the copy stream while the kernel runs; after
+// each chunk the copy engine advances a progress word in device memory (an 8-byte copy from pinned memory -- no SM
+// is involved, so a kernel that fills every SM cannot block it) and a warp that takes candidates beyond the
+// progress mark waits for it (bounded: a wait that times out fails the call). Results return after the kernel.
 int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long long n, int m, const OutStage& o) {
-  // A chunk must stay several waves of lanes deep (148 SMs x 512 lanes), or the tail of each launch costs more than
-  // the overlap wins: measured on C3, 2^18-candidate chunks beat both 2^17 and one monolithic copy-then-launch.
-  long long chunk = ctx->chunk_override > 0 ? ctx->chunk_override : (n + 3) / 4;
-  if (chunk < (1 << 18) && ctx->chunk_override <= 0) chunk = 1 << 18;
+  long long chunk = ctx->chunk_override > 0 ? ctx->chunk_override : (n + 31) / 32;
+  if (chunk < 16384) chunk = 16384;  // the kernel can start once the first chunk is in: keep it small
+  if ((n + chunk - 1) / chunk > kMaxChunks) chunk = (n + kMaxChunks - 1) / kMaxChunks;
   chunk = (chunk + 255) / 256 * 256;
-  const CheckParams full = cc.p;
-  cudaStream_t cs = ctx->stream, hs = ctx->h2d_stream, ds = ctx->d2h_stream;
+  cudaStream_t cs = ctx->stream, hs = ctx->h2d_stream;
   RQCD_CU(cudaEventRecord(ctx->ev_start, cs));  // copies must not overtake earlier work queued on the compute stream
   RQCD_CU(cudaStreamWaitEvent(hs, ctx->ev_start, 0));
-  RQCD_CU(cudaStreamWaitEvent(ds, ctx->ev_start, 0));
-  int ci = 0;
-  for (long long c0 = 0; c0 < n || ci == 0; c0 += chunk, ci++) {
-    const long long c1 = (c0 + chunk < n) ? c0 + chunk : n;
+  RQCD_CU(cudaMemsetAsync(ctx->d_stream, 0, 2 * sizeof(unsigned long long), hs));
+  auto copy_chunk = [&](int ci, long long c0, long long c1) -> cudaError_t {
     const long long w = c1 - c0;
-    if (w > 0) {
-      for (int b = 0; b < cc.nblocks; b++) {
-        const RowBlock& rb = cc.blocks[b];
-        RQCD_CU(cudaMemcpy2DAsync(rb.dst + c0, (size_t)n * 8, rb.src + c0, (size_t)rb.src_stride * 8, (size_t)w * 8,
-                                  rb.rows, cudaMemcpyHostToDevice, hs));
-      }
+    for (int b = 0; b < cc.nblocks && w > 0; b++) {
+      const RowBlock& rb = cc.blocks[b];
+      cudaError_t e = cudaMemcpy2DAsync(rb.dst + c0, (size_t)n * 8, rb.src + c0, (size_t)rb.src_stride * 8,
+                                        (size_t)w * 8, rb.rows, cudaMemcpyHostToDevice, hs);
+      if (e != cudaSuccess) return e;
     }
-    RQCD_CU(cudaEventRecord(ctx->ev_in[ci & 1], hs));
-    RQCD_CU(cudaStreamWaitEvent(cs, ctx->ev_in[ci & 1], 0));
-    slice_params(cc.p, full, c0, c1, m);
-    int st = run_check(ctx, cc, ci > 0);
-    if (st != RQCD_OK) return st;
-    if (w > 0) {
-      RQCD_CU(cudaEventRecord(ctx->ev_done, cs));
-      RQCD_CU(cudaStreamWaitEvent(ds, ctx->ev_done, 0));
-      if (o.verdict) RQCD_CU(cudaMemcpyAsync(out->verdict + c0, o.verdict + c0, (size_t)w, cudaMemcpyDeviceToHost, ds));
-      if (o.first)
-        RQCD_CU(cudaMemcpyAsync(out->first_obstacle + c0, o.first + c0, (size_t)w * 4, cudaMemcpyDeviceToHost, ds));
-      if (o.matrix && m > 0)
-        RQCD_CU(cudaMemcpyAsync(out->verdict_matrix + c0 * m, o.matrix + c0 * m, (size_t)w * (size_t)m,
-                                cudaMemcpyDeviceToHost, ds));
-      if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost + c0, o.cost + c0, (size_t)w * 8, cudaMemcpyDeviceToHost, ds));
-      if (o.coeffs)
-        RQCD_CU(cudaMemcpy2DAsync(out->coeffs + c0, (size_t)out->coeff_stride * 8, o.coeffs + c0, (size_t)n * 8,
-                                  (size_t)w * 8, RQCD_COEFF_ROWS, cudaMemcpyDeviceToHost, ds));
-    }
-    if (c1 >= n) break;
+    ctx->h_stream[ci] = (unsigned long long)c1;
+    return cudaMemcpyAsync(ctx->d_stream, ctx->h_stream + ci, sizeof(unsigned long long), cudaMemcpyHostToDevice, hs);
+  };
+  const long long first_end = chunk < n ? chunk : n;
+  RQCD_CU(copy_chunk(0, 0, first_end));
+  RQCD_CU(cudaEventRecord(ctx->ev_in[0], hs));
+  RQCD_CU(cudaStreamWaitEvent(cs, ctx->ev_in[0], 0));
+  cc.p.progress = ctx->d_stream;
+  cc.p.stream_error = ctx->d_stream + 1;
+  int st = run_check(ctx, cc);
+  cc.p.progress = nullptr;
+  cc.p.stream_error = nullptr;
+  if (st != RQCD_OK) return st;
+  int ci = 1;
+  for (long long c0 = first_end; c0 < n; c0 += chunk, ci++) RQCD_CU(copy_chunk(ci, c0, c0 + chunk < n ? c0 + chunk : n));
+  if (n > 0) {
+    if (o.verdict) RQCD_CU(cudaMemcpyAsync(out->verdict, o.verdict, (size_t)n, cudaMemcpyDeviceToHost, cs));
+    if (o.first) RQCD_CU(cudaMemcpyAsync(out->first_obstacle, o.first, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
+    if (o.matrix && m > 0)
+      RQCD_CU(cudaMemcpyAsync(out->verdict_matrix, o.matrix, (size_t)n * (size_t)m, cudaMemcpyDeviceToHost, cs));
+    if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost, o.cost, (size_t)n * 8, cudaMemcpyDeviceToHost, cs));
+    if (o.coeffs) RQCD_CU(rows_d2h(out->coeffs, out->coeff_stride, o.coeffs, n, RQCD_COEFF_ROWS, cs));
   }
-  cc.p = full;
-  RQCD_CU(cudaStreamSynchronize(ds));
+  RQCD_CU(cudaMemcpyAsync(ctx->h_stream + kMaxChunks, ctx->d_stream + 1, sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost, cs));
+  RQCD_CU(cudaStreamSynchronize(cs));
+  RQCD_CU(cudaStreamSynchronize(hs));
+  if (ctx->h_stream[kMaxChunks] != 0) {
+    snprintf(ctx->last_error, sizeof ctx->last_error, "streaming input: a chunk did not arrive within the time-out");
+    return RQCD_ERR_CUDA;
+  }
   return RQCD_OK;
 }
 
@@ -392,6 +383,8 @@ int rqcd_create(rqcd_ctx** out, int device) {
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counter, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_summary, sizeof(DevSummary));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_summary, sizeof(DevSummary));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stream, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_stream, (kMaxChunks + 1) * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     rqcd_destroy(ctx);
     return RQCD_ERR_CUDA;
@@ -417,6 +410,8 @@ void rqcd_destroy(rqcd_ctx* ctx) {
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_summary) cudaFree(ctx->d_summary);
   if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
+  if (ctx->d_stream) cudaFree(ctx->d_stream);
+  if (ctx->h_stream) cudaFreeHost(ctx->h_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);

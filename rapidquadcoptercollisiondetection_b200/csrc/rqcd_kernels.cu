@@ -68,6 +68,10 @@ RQCD_DEV bool better(double ca, long long ia, double cb, long long ib) {
   return ca < cb || (ca == cb && ia < ib);
 }
 
+// Inputs are read once and may still be arriving over PCIe while the kernel runs (CheckParams::progress): load
+// them at L2 (ld.global.cg), the coherence point with the copy engine, never through a possibly stale L1 line.
+RQCD_DEV double ld_in(const double* p) { return __ldcg(p); }
+
 // ---- trajectory construction for one lane ------------------------------------------------------------
 template <int MODE>
 RQCD_DEV void load_trajectory(const CheckParams& p, long long i, double (&c)[18], double& t0, double& t1,
@@ -75,12 +79,12 @@ RQCD_DEV void load_trajectory(const CheckParams& p, long long i, double (&c)[18]
   if (MODE == MODE_BC) {
     const double* d = p.in;
     const long long s = p.in_stride;
-    const double Tf = d[18 * s + i];
+    const double Tf = ld_in(d + 18 * s + i);
     double total = 0.0;
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
-      const double p0 = d[(0 + ax) * s + i], v0 = d[(3 + ax) * s + i], a0 = d[(6 + ax) * s + i];
-      const double pf = d[(9 + ax) * s + i], vf = d[(12 + ax) * s + i], af = d[(15 + ax) * s + i];
+      const double p0 = ld_in(d + (0 + ax) * s + i), v0 = ld_in(d + (3 + ax) * s + i), a0 = ld_in(d + (6 + ax) * s + i);
+      const double pf = ld_in(d + (9 + ax) * s + i), vf = ld_in(d + (12 + ax) * s + i), af = ld_in(d + (15 + ax) * s + i);
       const AxisParams q = gen_axis(p0, v0, a0, pf, vf, af, (p.goal_mask >> (3 * ax)) & 1,
                                     (p.goal_mask >> (3 * ax + 1)) & 1, (p.goal_mask >> (3 * ax + 2)) & 1, Tf);
       axis_coeffs(q, p0, v0, a0, c[0 + ax], c[3 + ax], c[6 + ax], c[9 + ax], c[12 + ax], c[15 + ax]);
@@ -91,10 +95,10 @@ RQCD_DEV void load_trajectory(const CheckParams& p, long long i, double (&c)[18]
     t1 = Tf;
   } else {
 #pragma unroll
-    for (int j = 0; j < 18; j++) c[j] = p.in[j * p.in_stride + i];
-    t0 = p.t_start ? p.t_start[i] : 0.0;
-    t1 = p.t_end[i];
-    cost = p.cost_in ? p.cost_in[i] : __longlong_as_double(0x7ff8000000000000ll);
+    for (int j = 0; j < 18; j++) c[j] = ld_in(p.in + j * p.in_stride + i);
+    t0 = p.t_start ? ld_in(p.t_start + i) : 0.0;
+    t1 = ld_in(p.t_end + i);
+    cost = p.cost_in ? ld_in(p.cost_in + i) : __longlong_as_double(0x7ff8000000000000ll);
   }
 }
 
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
 
   int n_have = 0;
   unsigned trip = 0;
+  unsigned long long avail = 0;  // candidates known to have arrived (streaming input)
   for (;;) {
 #if RQCD_LOCKSTEP == 1
     // ---- CTA barrier once per trip: the warps of a CTA walk the (larger than the 32 KB instruction cache) loop
@@ -163,9 +168,28 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         if (lane == 0) b = atomicAdd(p.work_counter, (unsigned long long)cnt);
         b = __shfl_sync(kFull, b, 0);
         if (b + (unsigned long long)cnt >= (unsigned long long)p.n) exhausted = true;
+        bool arrived = true;
+        if (p.progress) {  // streaming input: wait until the copy engine has delivered everything this warp took
+          unsigned long long want = b + (unsigned long long)cnt;
+          if (want > (unsigned long long)p.n) want = (unsigned long long)p.n;
+          if (want > avail) {
+            const long long t_begin = clock64();
+            for (;;) {
+              avail = *reinterpret_cast<const volatile unsigned long long*>(p.progress);
+              if (avail >= want) break;
+              if (clock64() - t_begin > (1ll << 32)) {  // ~2 s: the copy never came; fail the call instead of hanging
+                if (lane == 0) atomicExch(p.stream_error, 1ull);
+                arrived = false;
+                exhausted = true;
+                break;
+              }
+              __nanosleep(256);
+            }
+          }
+        }
         if (!have) {
           const long long i = (long long)b + __popc(need & lt_mask);
-          if (i < p.n) {
+          if (i < p.n && arrived) {
             idx = i;
             double t0, t1, cost;
             load_trajectory<MODE>(p, i, c, t0, t1, cost);
@@ -189,10 +213,10 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
               RQCD_SLOT(SLOT_X1 + 0) = e.x, RQCD_SLOT(SLOT_X1 + 1) = e.y, RQCD_SLOT(SLOT_X1 + 2) = e.z;
             }
             if (PAIRWISE) {
-              sph.cx = p.spheres[i];
-              sph.cy = p.spheres[p.sphere_stride + i];
-              sph.cz = p.spheres[2 * p.sphere_stride + i];
-              sph.r = p.spheres[3 * p.sphere_stride + i];
+              sph.cx = ld_in(p.spheres + i);
+              sph.cy = ld_in(p.spheres + p.sphere_stride + i);
+              sph.cz = ld_in(p.spheres + 2 * p.sphere_stride + i);
+              sph.r = ld_in(p.spheres + 3 * p.sphere_stride + i);
             }
             have = true;
             in_pair = false;

@@ -61,6 +61,10 @@ struct CheckParams {
   int refill_min;          // idle lanes per warp that trigger a work-queue fetch
   unsigned long long* work_counter;
   BlockPartial* partials;  // [gridDim.x]
+  // streaming input (host-pointer calls): candidates [0, *progress) have arrived in `in`; null = all present.
+  // The copy engine advances *progress after each chunk; *stream_error is set if a wait times out.
+  const unsigned long long* progress;
+  unsigned long long* stream_error;
 };
 
 size_t check_smem_bytes(int mp, int nfields, bool moving);
