@@ -275,8 +275,18 @@ int validate_out(const rqcd_out* out, uint32_t flags, long long n) {
 // is involved, so a kernel that fills every SM cannot block it) and a warp that takes candidates beyond the
 // progress mark waits for it (bounded: a wait that times out fails the call). Results return after the kernel.
 int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long long n, int m, const OutStage& o) {
+  // Streaming needs the copies to run on the copy engines while the kernel holds every SM. That is the case for
+  // page-locked host memory; a pitched copy from PAGEABLE memory may be finished by a driver kernel, which could not
+  // be scheduled next to the waiting persistent kernel -- so pageable input is copied completely before the launch.
+  bool pinned = true;
+  for (int b = 0; b < cc.nblocks; b++) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, cc.blocks[b].src) != cudaSuccess || at.type != cudaMemoryTypeHost) pinned = false;
+  }
+  cudaGetLastError();
   long long chunk = ctx->chunk_override > 0 ? ctx->chunk_override : (n + 31) / 32;
   if (chunk < 16384) chunk = 16384;  // the kernel can start once the first chunk is in: keep it small
+  if (!pinned) chunk = n > 0 ? n : 1;
   if ((n + chunk - 1) / chunk > kMaxChunks) chunk = (n + kMaxChunks - 1) / kMaxChunks;
   chunk = (chunk + 255) / 256 * 256;
   cudaStream_t cs = ctx->stream, hs = ctx->h2d_stream;
