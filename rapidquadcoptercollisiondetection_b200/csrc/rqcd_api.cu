@@ -56,7 +56,7 @@ struct rqcd_ctx {
   bool summary_valid = false;
   // staging for host-pointer calls
   DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group;
-  int refill_min = 4;
+  int refill_min = 0;  // RQCD_REFILL_MIN override; 0 = chosen from the obstacle count
   unsigned long long launches = 0;
   char last_error[512] = {0};
 };
@@ -179,7 +179,10 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc, bool accumulate = false) {
   p.m = cc.pairwise ? 1 : ctx->m;
   p.mp = ctx->mp;
   p.nfields = ctx->nfields;
-  p.refill_min = ctx->refill_min;
+  // idle lanes per warp (CTA average) that trigger a work-queue fetch: a fetch costs a divergent generate pass, an
+  // idle lane costs a slot in every frame until then; trajectories over many obstacles finish rarely, so they fetch
+  // eagerly (measured optima on B200: 2 at M = 256, 4 at M = 64, 8 at M = 5)
+  p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (p.m >= 128 ? 2 : (p.m >= 16 ? 4 : 8));
   p.work_counter = ctx->d_counter;
   const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->nfields, moving);
   if (smem > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
