@@ -42,7 +42,7 @@ struct rqcd_ctx {
   long long chunk_override = 0;                              // RQCD_HOST_CHUNK: candidates per chunk (0 = automatic)
   cudaDeviceProp prop;
   // obstacle set
-  int m = 0, mp = 0, nfields = OF_STATIC_FIELDS;
+  int m = 0, mp = 0, stride = OF_STATIC_FIELDS;  // record stride in doubles (odd)
   bool any_moving = false;
   DevBuf obs_blob;
   // launch scratch
@@ -178,13 +178,13 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc, bool accumulate = false) {
   p.obs_blob = ctx->obs_blob.p;
   p.m = cc.pairwise ? 1 : ctx->m;
   p.mp = ctx->mp;
-  p.nfields = ctx->nfields;
+  p.stride = ctx->stride;
   // idle lanes per warp (CTA average) that trigger a work-queue fetch: a fetch costs a divergent generate pass, an
   // idle lane costs a slot in every frame until then; trajectories over many obstacles finish rarely, so they fetch
   // eagerly (measured optima on B200: 2 at M = 256, 4 at M = 64, 8 at M = 5)
   p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (p.m >= 128 ? 2 : (p.m >= 16 ? 4 : 8));
   p.work_counter = ctx->d_counter;
-  const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->nfields, moving);
+  const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->stride, moving);
   if (smem > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
   RQCD_CU(check_prepare(cc.mode, moving, cc.pairwise, smem));
   int per_sm = check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, smem);
@@ -492,16 +492,16 @@ int rqcd_set_obstacles(rqcd_ctx* ctx, const rqcd_obstacle* obstacles, int32_t m)
     if (st != RQCD_OK) return st;
     any_moving = any_moving || obstacles[k].moving;
   }
-  const int nfields = any_moving ? OF_MOVING_FIELDS : OF_STATIC_FIELDS;
+  const int stride = (any_moving ? OF_MOVING_FIELDS : OF_STATIC_FIELDS) | 1;  // odd: bank spread, see rqcd_device.cuh
   const int mp = (m + 3) / 4 * 4;
-  if (check_smem_bytes(mp, nfields, any_moving) > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
-  const size_t bytes = (size_t)nfields * mp * 8 + (size_t)mp * 4;
+  if (check_smem_bytes(mp, stride, any_moving) > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
+  const size_t bytes = (size_t)stride * mp * 8 + (size_t)mp * 4;
   std::vector<unsigned char> blob(bytes > 0 ? bytes : 16, 0);
   double* tab = reinterpret_cast<double*>(blob.data());
-  int* fl = reinterpret_cast<int*>(blob.data() + (size_t)nfields * mp * 8);
+  int* fl = reinterpret_cast<int*>(blob.data() + (size_t)stride * mp * 8);
   for (int k = 0; k < m; k++) {
     const rqcd_obstacle& o = obstacles[k];
-    auto F = [&](int f) -> double& { return tab[(size_t)f * mp + k]; };
+    auto F = [&](int f) -> double& { return tab[(size_t)k * stride + f]; };
     F(OF_CX) = o.center[0];
     F(OF_CY) = o.center[1];
     F(OF_CZ) = o.center[2];
@@ -537,7 +537,7 @@ int rqcd_set_obstacles(rqcd_ctx* ctx, const rqcd_obstacle* obstacles, int32_t m)
   RQCD_CU(cudaMemcpy(ctx->obs_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   ctx->m = m;
   ctx->mp = mp;
-  ctx->nfields = nfields;
+  ctx->stride = stride;
   ctx->any_moving = any_moving;
   return RQCD_OK;
 }

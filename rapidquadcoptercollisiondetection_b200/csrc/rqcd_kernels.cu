@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   const int m = PAIRWISE ? 1 : p.m, mp = p.mp;
 
   double* tab = reinterpret_cast<double*>(smem_raw);
-  int* oflags = reinterpret_cast<int*>(tab + (size_t)p.nfields * mp);
+  int* oflags = reinterpret_cast<int*>(tab + (size_t)p.stride * mp);
   unsigned long long* wcnt = reinterpret_cast<unsigned long long*>(oflags + mp);  // [kWarps][8]
   double* bcost = reinterpret_cast<double*>(wcnt + kWarps * 8);                   // [kThreads]
   long long* bidx = reinterpret_cast<long long*>(bcost + kThreads);               // [kThreads]
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   __shared__ __align__(8) uint64_t mbar;
 #define RQCD_SLOT(row) slot[(row) * kThreads + tid]
 
-  const uint32_t blob_bytes = (uint32_t)(((size_t)p.nfields * mp) * 8 + (size_t)mp * 4);
+  const uint32_t blob_bytes = (uint32_t)(((size_t)p.stride * mp) * 8 + (size_t)mp * 4);
   if (tid == 0) mbar_init(&mbar, 1);
   if (tid < kWarps * 8) wcnt[tid] = 0ull;
   bcost[tid] = __longlong_as_double(0x7ff0000000000000ll);
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   double ts = 0, tf = 0;
   V3 Xs = v3(0, 0, 0), Xf = v3(0, 0, 0);
   int k = 0, verdict = 0, first = -1, sp = 0;
+  unsigned pair_hits = 0, depth_cap_hits = 0;  // this trajectory's pairs: Collision | Indeterminable << 16; verdict 3
   double2 stack[kMaxDepth][4];  // {ts, lo_tf}, {Xs.x, Xs.y}, {Xs.z, lo_x.x}, {lo_x.y, lo_x.z}
   LaneSphere sph;
   sph.cx = sph.cy = sph.cz = sph.r = 0;
@@ -251,9 +252,10 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         // Trajectory::operator- (Trajectory.hpp:121-128): coefficient-wise difference on the common window
         const int fl = oflags[k];
         if (fl & OBS_MOVING) {
+          const double* rec = tab + (size_t)k * p.stride;
 #pragma unroll
-          for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid] - tab[(OF_MOTION + j) * mp + k];
-          const double ms = tab[OF_MT0 * mp + k], me = tab[OF_MT1 * mp + k];
+          for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid] - rec[OF_MOTION + j];
+          const double ms = rec[OF_MT0], me = rec[OF_MT1];
           const double t0 = ts, t1 = tf;
           ts = (t0 < ms) ? ms : t0;  // std::max(_startTime, rhs start)
           tf = (me < t1) ? me : t1;  // std::min(_endTime, rhs end)
@@ -282,10 +284,9 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         r = frame(c, ts, tf, Xs, Xf, first_frame, sph, p.min_t, ch);
       } else {
         TableObs o;
-        o.tab = tab;
-        o.mp = mp;
-        o.k = min(k, max(m - 1, 0));
-        o.flags = oflags[o.k];
+        const int kk = min(k, max(m - 1, 0));
+        o.rec = tab + (size_t)kk * p.stride;
+        o.flags = oflags[kk];
         r = frame(c, ts, tf, Xs, Xf, first_frame, o, p.min_t, ch);
       }
       first_frame = false;
@@ -322,20 +323,26 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
       }
     }
 
-    // ---- bookkeeping for completed pairs / trajectories
+    // ---- bookkeeping. A finished pair only bumps the lane's packed per-trajectory counters; the CTA counters in
+    // shared memory are touched once per finished trajectory
     if (pv >= 0) {
       if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)pv;
       if (pv != 0 && first < 0) {
         verdict = pv;
         first = k;
       }
+      pair_hits += (pv == 1 ? 1u : 0u) + (pv == 2 ? 0x10000u : 0u);
+      depth_cap_hits += (pv == 3);
       k++;
     }
     const bool fin = have && !in_pair && (k >= m || (p.early_exit && verdict != 0));
-    const int tv = fin ? verdict : -1;
-    {
-      const unsigned p0 = __ballot_sync(kFull, pv == 0), p1 = __ballot_sync(kFull, pv == 1);
-      const unsigned p2 = __ballot_sync(kFull, pv == 2), p3 = __ballot_sync(kFull, pv == 3);
+    if (__any_sync(kFull, fin)) {
+      // warp-level sums of the finishing lanes' counters (REDUX), one shared-memory update by lane 0
+      const unsigned n1 = fin ? (pair_hits & 0xffffu) : 0u, n2 = fin ? (pair_hits >> 16) : 0u;  // k <= m < 2^16
+      const unsigned n3 = fin ? depth_cap_hits : 0u, nk = fin ? (unsigned)k : 0u;
+      const unsigned s1 = __reduce_add_sync(kFull, n1), s2 = __reduce_add_sync(kFull, n2);
+      const unsigned s3 = __reduce_add_sync(kFull, n3), sk = __reduce_add_sync(kFull, nk);
+      const int tv = fin ? verdict : -1;
       const unsigned q0 = __ballot_sync(kFull, tv == 0), q1 = __ballot_sync(kFull, tv == 1);
       const unsigned q2 = __ballot_sync(kFull, tv == 2), q3 = __ballot_sync(kFull, tv == 3);
       if (lane == 0) {
@@ -344,21 +351,23 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         w[1] += __popc(q1);
         w[2] += __popc(q2);
         w[3] += __popc(q3);
-        w[4] += __popc(p0);
-        w[5] += __popc(p1);
-        w[6] += __popc(p2);
-        w[7] += __popc(p3);
+        w[4] += sk - s1 - s2 - s3;
+        w[5] += s1;
+        w[6] += s2;
+        w[7] += s3;
       }
-    }
-    if (fin) {
-      if (p.verdict) p.verdict[idx] = (uint8_t)verdict;
-      if (p.first_obstacle) p.first_obstacle[idx] = first;
-      const double cost = RQCD_SLOT(SLOT_COST);
-      if (verdict == 0 && cost < bcost[tid]) {  // indices handed to one lane ascend, so ties keep the lowest
-        bcost[tid] = cost;
-        bidx[tid] = p.index_base + idx;
+      if (fin) {
+        if (p.verdict) p.verdict[idx] = (uint8_t)verdict;
+        if (p.first_obstacle) p.first_obstacle[idx] = first;
+        const double cost = RQCD_SLOT(SLOT_COST);
+        if (verdict == 0 && cost < bcost[tid]) {  // indices handed to one lane ascend, so ties keep the lowest
+          bcost[tid] = cost;
+          bidx[tid] = p.index_base + idx;
+        }
+        have = false;
+        pair_hits = 0;
+        depth_cap_hits = 0;
       }
-      have = false;
     }
   }
 #undef RQCD_SLOT
@@ -717,8 +726,8 @@ int grid_for(long long n, int cap) {
 
 }  // namespace
 
-size_t check_smem_bytes(int mp, int nfields, bool moving) {
-  size_t b = (size_t)nfields * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
+size_t check_smem_bytes(int mp, int stride, bool moving) {
+  size_t b = (size_t)stride * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
   b += (kThreads / 32) * 8 * 8;                           // warp counters
   b += (size_t)kThreads * 16;                             // best cost / index per thread
   b += (size_t)kThreads * 8 * 9;                          // t0, t1, cost, X(t0), X(t1) per thread (SlotRow)
@@ -741,13 +750,13 @@ int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, size_t smem) {
 
 cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
                          DevSummary* d_summary, bool accumulate) {
-  const size_t smem = check_smem_bytes(pairwise ? 0 : p.mp, pairwise ? 0 : p.nfields, moving);
+  const size_t smem = check_smem_bytes(pairwise ? 0 : p.mp, pairwise ? 0 : p.stride, moving);
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
   CheckParams q = p;
   if (pairwise) {
     q.mp = 0;
-    q.nfields = 0;
+    q.stride = 0;
   }
   void* args[] = {&q};
   e = cudaLaunchKernel(select_check(mode, moving, pairwise), dim3(grid), dim3(kThreads), args, smem, s);

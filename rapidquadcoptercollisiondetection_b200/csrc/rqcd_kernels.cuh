@@ -46,9 +46,9 @@ struct CheckParams {
   long long n;
   long long index_base;
   double min_t;
-  // obstacle table blob in global memory: nfields*mp doubles followed by mp int flags
+  // obstacle table blob in global memory: mp records of `stride` doubles (stride odd), then mp int flags
   const void* obs_blob;
-  int m, mp, nfields;
+  int m, mp, stride;
   // outputs, each may be null
   uint8_t* verdict;
   int* first_obstacle;
@@ -67,7 +67,7 @@ struct CheckParams {
   unsigned long long* stream_error;
 };
 
-size_t check_smem_bytes(int mp, int nfields, bool moving);
+size_t check_smem_bytes(int mp, int stride, bool moving);
 // Returns the number of kernels launched (2: check + finalize) or a negative cudaError.
 cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
                          DevSummary* d_summary, bool accumulate);
