@@ -59,7 +59,8 @@ RQCD_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-enum SlotRow { SLOT_T0 = 0, SLOT_T1, SLOT_COST, SLOT_X0, SLOT_X1 = SLOT_X0 + 3, kSlotRows = SLOT_X1 + 3 };  // per-thread smem
+enum SlotRow { SLOT_T0 = 0, SLOT_T1, SLOT_COST, SLOT_X0, SLOT_X1 = SLOT_X0 + 3, SLOT_XS = SLOT_X1 + 3,  // EndPoints rows start here
+               kSlotRows = SLOT_XS + EndPoints::kRows };  // per-thread shared-memory rows
 
 RQCD_DEV bool better(double ca, long long ia, double cb, long long ib) {
   // candidate a beats b: lower cost, or equal cost and lower index; an empty slot has index -1
@@ -138,7 +139,11 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
 #pragma unroll
   for (int j = 0; j < 18; j++) c[j] = 0.0;
   double ts = 0, tf = 0;
-  V3 Xs = v3(0, 0, 0), Xf = v3(0, 0, 0);
+  EndPoints ends;
+  ends.slot = slot + SLOT_XS * kThreads + tid;
+  ends.stride = kThreads;
+  ends.set_xs(v3(0, 0, 0));
+  ends.set_xf(v3(0, 0, 0));
   int k = 0, verdict = 0, first = -1, sp = 0;
   unsigned pair_hits = 0, depth_cap_hits = 0;  // this trajectory's pairs: Collision | Indeterminable << 16; verdict 3
   double2 stack[kMaxDepth][4];  // {ts, lo_tf}, {Xs.x, Xs.y}, {Xs.z, lo_x.x}, {lo_x.y, lo_x.z}
@@ -267,11 +272,11 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
 #pragma unroll
           for (int j = 0; j < 18; j++) c[j] = base[j * kThreads + tid];
         }
-        Xs = traj_value(c, ts);
-        Xf = traj_value(c, tf);
+        ends.set_xs(traj_value(c, ts));
+        ends.set_xf(traj_value(c, tf));
       } else {
-        Xs = v3(RQCD_SLOT(SLOT_X0 + 0), RQCD_SLOT(SLOT_X0 + 1), RQCD_SLOT(SLOT_X0 + 2));
-        Xf = v3(RQCD_SLOT(SLOT_X1 + 0), RQCD_SLOT(SLOT_X1 + 1), RQCD_SLOT(SLOT_X1 + 2));
+        ends.set_xs(v3(RQCD_SLOT(SLOT_X0 + 0), RQCD_SLOT(SLOT_X0 + 1), RQCD_SLOT(SLOT_X0 + 2)));
+        ends.set_xf(v3(RQCD_SLOT(SLOT_X1 + 0), RQCD_SLOT(SLOT_X1 + 1), RQCD_SLOT(SLOT_X1 + 2)));
       }
     }
 
@@ -281,13 +286,13 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
       Children ch;
       int r;
       if (PAIRWISE) {
-        r = frame(c, ts, tf, Xs, Xf, first_frame, sph, p.min_t, ch);
+        r = frame(c, ts, tf, ends, first_frame, sph, p.min_t, ch);
       } else {
         TableObs o;
         const int kk = min(k, max(m - 1, 0));
         o.rec = tab + (size_t)kk * p.stride;
         o.flags = oflags[kk];
-        r = frame(c, ts, tf, Xs, Xf, first_frame, o, p.min_t, ch);
+        r = frame(c, ts, tf, ends, first_frame, o, p.min_t, ch);
       }
       first_frame = false;
       // state update, written with selects: one instruction stream for the common cases (no child; one child)
@@ -296,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
       const bool clear = in_pair & (r == STEP_CLEAR);
       if (to_hi & ch.has_lo) {  // both children: the parent's low tail call waits until the high subtree is clear
         if (sp < kMaxDepth) {
+          const V3 Xs = ends.xs();
           stack[sp][0] = make_double2(ts, ch.lo_tf);
           stack[sp][1] = make_double2(Xs.x, Xs.y);
           stack[sp][2] = make_double2(Xs.z, ch.lo_x.x);
@@ -307,16 +313,16 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         }
       }
       ts = to_hi ? ch.t_next : ts;
-      Xs = v3(to_hi ? ch.x_next.x : Xs.x, to_hi ? ch.x_next.y : Xs.y, to_hi ? ch.x_next.z : Xs.z);
       tf = to_lo ? ch.t_next : tf;
-      Xf = v3(to_lo ? ch.x_next.x : Xf.x, to_lo ? ch.x_next.y : Xf.y, to_lo ? ch.x_next.z : Xf.z);
+      if (to_hi) ends.set_xs(ch.x_next);
+      if (to_lo) ends.set_xf(ch.x_next);
       if (clear & (sp > 0)) {  // subtree clear: resume the innermost parked low child
         --sp;
         const double2 e0 = stack[sp][0], e1 = stack[sp][1], e2 = stack[sp][2], e3 = stack[sp][3];
         ts = e0.x;
         tf = e0.y;
-        Xs = v3(e1.x, e1.y, e2.x);
-        Xf = v3(e2.y, e3.x, e3.y);
+        ends.set_xs(v3(e1.x, e1.y, e2.x));
+        ends.set_xf(v3(e2.y, e3.x, e3.y));
       } else if (in_pair & !child) {  // NoCollision with nothing parked, Collision or Indeterminable: the pair is done
         pv = clear ? 0 : r;
         in_pair = false;
@@ -730,7 +736,7 @@ size_t check_smem_bytes(int mp, int stride, bool moving) {
   size_t b = (size_t)stride * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
   b += (kThreads / 32) * 8 * 8;                           // warp counters
   b += (size_t)kThreads * 16;                             // best cost / index per thread
-  b += (size_t)kThreads * 8 * 9;                          // t0, t1, cost, X(t0), X(t1) per thread (SlotRow)
+  b += (size_t)kThreads * 8 * (9 + EndPoints::kRows);     // t0, t1, cost, X(t0), X(t1) + the frame's rows (SlotRow)
   if (moving) b += (size_t)18 * kThreads * 8;             // the lane's own coefficients
   return b;
 }
