@@ -59,8 +59,11 @@ RQCD_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-enum SlotRow { SLOT_T0 = 0, SLOT_T1, SLOT_COST, SLOT_X0, SLOT_X1 = SLOT_X0 + 3, SLOT_XS = SLOT_X1 + 3,  // EndPoints rows start here
-               kSlotRows = SLOT_XS + EndPoints::kRows };  // per-thread shared-memory rows
+// Per-trajectory constants (window, cost, X(t_start), X(t_end)) are read once per obstacle: they live in a
+// volatile per-thread local array (L1-resident), not in registers and not in shared memory, which is kept for the
+// obstacle table and the frame's rows so that two CTAs fit next to a 256-obstacle table.
+enum TrajRow { SLOT_T0 = 0, SLOT_T1, SLOT_COST, SLOT_X0, SLOT_X1 = SLOT_X0 + 3, kTrajRows = SLOT_X1 + 3 };
+constexpr int kSlotRows = EndPoints::kRows;  // per-thread shared-memory rows
 
 RQCD_DEV bool better(double ca, long long ia, double cb, long long ib) {
   // candidate a beats b: lower cost, or equal cost and lower index; an empty slot has index -1
@@ -118,7 +121,8 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   double* slot = reinterpret_cast<double*>(bidx + kThreads);                      // [kSlotRows][kThreads], see SlotRow
   double* base = slot + kSlotRows * kThreads;                                     // MOVING: [18][kThreads]
   __shared__ __align__(8) uint64_t mbar;
-#define RQCD_SLOT(row) slot[(row) * kThreads + tid]
+  volatile double traj_const[kTrajRows];
+#define RQCD_SLOT(row) traj_const[row]
 
   const uint32_t blob_bytes = (uint32_t)(((size_t)p.stride * mp) * 8 + (size_t)mp * 4);
   if (tid == 0) mbar_init(&mbar, 1);
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   for (int j = 0; j < 18; j++) c[j] = 0.0;
   double ts = 0, tf = 0;
   EndPoints ends;
-  ends.slot = slot + SLOT_XS * kThreads + tid;
+  ends.slot = slot + tid;
   ends.stride = kThreads;
   ends.set_xs(v3(0, 0, 0));
   ends.set_xf(v3(0, 0, 0));
@@ -736,7 +740,7 @@ size_t check_smem_bytes(int mp, int stride, bool moving) {
   size_t b = (size_t)stride * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
   b += (kThreads / 32) * 8 * 8;                           // warp counters
   b += (size_t)kThreads * 16;                             // best cost / index per thread
-  b += (size_t)kThreads * 8 * (9 + EndPoints::kRows);     // t0, t1, cost, X(t0), X(t1) + the frame's rows (SlotRow)
+  b += (size_t)kThreads * 8 * EndPoints::kRows;           // X(ts), X(tf) and the frame's evaluated positions
   if (moving) b += (size_t)18 * kThreads * 8;             // the lane's own coefficients
   return b;
 }
