@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <limits>
 #include <memory>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -190,12 +191,13 @@ class Batch {
     std::vector<uint8_t> verdict;         // CollisionChecker::CollisionResult per candidate (first hit in index order)
     std::vector<int32_t> first_obstacle;  // -1 when collision free
     std::vector<double> cost;             // RapidTrajectoryGenerator::GetCost()
+    std::vector<double> coeffs;           // only when asked for: RQCD_COEFF_ROWS x n, GetTrajectory() coefficients
     rqcd_summary summary;
   };
 
   // bc: RQCD_BC_ROWS x n, row r at bc + r*n (host memory). earlyExit = ForestPerformanceEval's inner break.
   Result GenerateAndCheck(const double* bc, int64_t n, double minTimeSection, uint32_t goalMask = RQCD_GOAL_ALL,
-                          bool earlyExit = false, int64_t indexBase = 0) {
+                          bool earlyExit = false, int64_t indexBase = 0, bool wantCoeffs = false) {
     Result r;
     r.verdict.resize(n);
     r.first_obstacle.resize(n);
@@ -206,6 +208,11 @@ class Batch {
     out.first_obstacle = r.first_obstacle.data();
     out.cost = r.cost.data();
     out.summary = &r.summary;
+    if (wantCoeffs) {
+      r.coeffs.resize((size_t)RQCD_COEFF_ROWS * n);
+      out.coeffs = r.coeffs.data();
+      out.coeff_stride = n;
+    }
     ctx_.check(rqcd_generate_check(ctx_.get(), &in, n, minTimeSection, earlyExit ? RQCD_F_EARLY_EXIT : 0, indexBase, &out),
                true);
     return r;
@@ -226,12 +233,65 @@ class Batch {
     return r;
   }
 
+  // RapidTrajectoryGenerator::CheckInputFeasibility for every candidate. group (n entries or nullptr): candidates with
+  // equal consecutive group ids share one generator object, as ForestPerformanceEval's batches do.
+  std::vector<uint8_t> InputFeasibility(const double* bc, int64_t n, const CommonMath::Vec3& gravity, double fminAllowed,
+                                        double fmaxAllowed, double wmaxAllowed, double minTimeSection,
+                                        const int64_t* group = nullptr, uint32_t goalMask = RQCD_GOAL_ALL) {
+    std::vector<uint8_t> res(n);
+    rqcd_bc_soa in = {bc, n, goalMask, 0};
+    const double g[3] = {gravity.x, gravity.y, gravity.z};
+    ctx_.check(rqcd_check_input_feasibility(ctx_.get(), &in, n, g, fminAllowed, fmaxAllowed, wmaxAllowed, minTimeSection,
+                                            group, 0, res.data()));
+    return res;
+  }
+
   int32_t NumObstacles() const { return m_; }
 
  private:
   Context& ctx_;
   int32_t m_ = 0;
 };
+
+}  // namespace rqcd
+
+namespace rqcd {
+
+// The on-disk formats of the reference's Forest driver, so that scripts/plotSingleForestBatch.py reads GPU output:
+// one row per candidate = 18 coefficients (t^5..t^0, xyz each), Tf, inputFeas, stateFeas, three per-call timings
+// [ns], every field followed by a comma, default ostream formatting (test/ForestPerformanceEval.cpp:255-267).
+// timings may be nullptr (a batched GPU call has no per-candidate times): zeros are written.
+inline void WriteForestBatchCsv(std::ostream& os, int64_t n, const double* coeffs, int64_t coeffStride, const double* Tf,
+                                const uint8_t* inputFeas, const uint8_t* stateFeas, const long* timingsNs = nullptr) {
+  for (int64_t i = 0; i < n; i++) {
+    for (int k = 0; k < RQCD_COEFF_ROWS; k++) os << coeffs[k * coeffStride + i] << ",";
+    os << Tf[i] << "," << (int)inputFeas[i] << "," << (int)stateFeas[i] << ",";
+    for (int k = 0; k < 3; k++) os << (timingsNs ? timingsNs[3 * i + k] : 0L) << ",";
+    os << "\n";
+  }
+}
+
+// One row per obstacle: centre, side lengths, row-major rotation matrix (ForestPerformanceEval.cpp:139-147).
+inline void WriteTreeParamsCsv(std::ostream& os, const std::vector<std::shared_ptr<CommonMath::ConvexObj>>& trees) {
+  for (auto& t : trees) {
+    const rqcd_obstacle o = t->Record();
+    const double* v = o.quat;  // printed to 6 digits: the matrix of Rotation.hpp:203-220
+    const double r0 = v[0] * v[0], r1 = v[1] * v[1], r2 = v[2] * v[2], r3 = v[3] * v[3];
+    const double R[9] = {r0 + r1 - r2 - r3,
+                         2 * v[1] * v[2] - 2 * v[0] * v[3],
+                         2 * v[1] * v[3] + 2 * v[0] * v[2],
+                         2 * v[1] * v[2] + 2 * v[0] * v[3],
+                         r0 - r1 + r2 - r3,
+                         2 * v[2] * v[3] - 2 * v[0] * v[1],
+                         2 * v[1] * v[3] - 2 * v[0] * v[2],
+                         2 * v[2] * v[3] + 2 * v[0] * v[1],
+                         r0 - r1 - r2 + r3};
+    for (int i = 0; i < 3; i++) os << o.center[i] << ",";
+    for (int i = 0; i < 3; i++) os << o.side[i] << ",";
+    for (int i = 0; i < 9; i++) os << R[i] << ",";
+    os << "\n";
+  }
+}
 
 }  // namespace rqcd
 

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <vector>
 
@@ -38,7 +39,19 @@ int main(int argc, char** argv) {
     rqcd::Context ctx(0);
     rqcd::Batch batch(ctx);
     batch.SetObstacles(obstacles);
-    rqcd::Batch::Result got = batch.GenerateAndCheck(bc.data(), n, minT, RQCD_GOAL_ALL, /*earlyExit=*/true);
+    rqcd::Batch::Result got = batch.GenerateAndCheck(bc.data(), n, minT, RQCD_GOAL_ALL, /*earlyExit=*/true, 0,
+                                                     /*wantCoeffs=*/true);
+    // the driver also calls CheckInputFeasibility(5, 30, 20, 0.002) on its per-batch generator object (:203-209)
+    std::vector<int64_t> group(n);
+    for (int64_t i = 0; i < n; i++) group[i] = i / perBatch;
+    std::vector<uint8_t> inputFeas = batch.InputFeasibility(bc.data(), n, Vec3(0, 0, -9.81), 5, 30, 20, 0.002, group.data());
+    if (argc > 2) {  // batch 0 in the driver's file formats (ForestPerformanceEval.cpp:139-147, 255-267)
+      std::ofstream csv(std::string(argv[2]) + "/ForestPerfEval.csv");
+      rqcd::WriteForestBatchCsv(csv, perBatch, got.coeffs.data(), n, bc.data() + (size_t)RQCD_BC_TF * n, inputFeas.data(),
+                                got.verdict.data());
+      std::ofstream trees(std::string(argv[2]) + "/ForestPerfEvaltreeParamsCSV.csv");
+      rqcd::WriteTreeParamsCsv(trees, obstacles);
+    }
 
     // ---- oracle on the same arrays
     rqcd_obstacle recs[5];

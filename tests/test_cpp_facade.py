@@ -34,9 +34,23 @@ def test_facade_compiles_and_refuses_without_gpu():
     assert "no CPU fallback" in r.stderr
 
 
+def _fmt(x):
+    return "%g" % x  # default ostream formatting of a double: 6 significant digits
+
+
 @pytest.mark.gpu
-def test_forest_loop_through_facade_matches_oracle():
+def test_forest_loop_through_facade_matches_oracle(tmp_path, forest_golden):
+    """... and the files it writes for batch 0 equal the reference's checked-in data/ForestPerfEval.csv (columns 1-21;
+    22-24 are wall-clock timings) and data/ForestPerfEvaltreeParamsCSV.csv field for field, as text."""
     _build()
-    r = subprocess.run([EXE, "50"], capture_output=True, text=True)
+    r = subprocess.run([EXE, "50", str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
     assert "mismatches 0" in r.stdout
+    rows = [ln.rstrip(",\n").split(",") for ln in open(tmp_path / "ForestPerfEval.csv")]
+    gold = forest_golden["csv"]
+    assert len(rows) == 100 and all(len(x) == 24 for x in rows)
+    for i, row in enumerate(rows):
+        want = [_fmt(v) for v in gold[i, :19]] + [str(int(gold[i, 19])), str(int(gold[i, 20]))]
+        assert row[:21] == want, (i, row[:21], want)
+    trees = [ln.rstrip(",\n").split(",") for ln in open(tmp_path / "ForestPerfEvaltreeParamsCSV.csv")]
+    assert [[_fmt(v) for v in t] for t in forest_golden["trees"]] == trees
