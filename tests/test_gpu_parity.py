@@ -236,3 +236,24 @@ def test_input_feasibility_forest_batches_match_reference_counts(ctx, oracle, ve
     got = ctx.input_feasibility(bc, group=group)
     assert int((got == 0).sum()) == golden_counts["c2_input_feasible"]
     np.testing.assert_array_equal(got, oracle.input_feasibility(bc, group=group))
+
+
+def test_reference_drivers_known_answers_at_full_size(ctx, oracle, golden_counts):
+    """The reference's checked-in outputs reproduced by the CUDA path on the drivers' own input streams:
+    data/PerformanceEval.txt:23-25 -> 9 600 380 / 399 612 / 8 of 10^7 accepted trials (pairwise spheres), and
+    data/ForestPerfEval.txt:28-29 -> 639 533 input feasible / 603 810 collision free of 10^6 (five prisms, early exit).
+    (The oracle only draws the inputs here -- mt19937 stream and acceptance filter; the counts come from the GPU.)"""
+    bc = oracle.c2_inputs(10_000, 100)
+    ctx.set_obstacles(abi.make_obstacles(W.forest_obstacles()), 5)
+    r = ctx.generate_check(bc, MIN_T, flags=abi.F_EARLY_EXIT, matrix=False)
+    assert r["summary"]["traj_counts"][0] == golden_counts["c2_collision_free"]
+    feas = ctx.input_feasibility(bc, group=np.repeat(np.arange(10_000, dtype=np.int64), 100))
+    assert int((feas == 0).sum()) == golden_counts["c2_input_feasible"]
+
+    n = golden_counts["c1_n"]
+    bc, sph, _ = oracle.c1_inputs(n, filter=True)
+    # the acceptance filter itself, on the device: every accepted trial is input feasible for a fresh generator
+    assert int((ctx.input_feasibility(bc[:, :500_000].copy()) != 0).sum()) == 0
+    r = ctx.generate_check_pairwise(bc, sph, MIN_T)
+    assert r["summary"]["traj_counts"][:3] == [golden_counts["c1_no_collision"], golden_counts["c1_collision"],
+                                              golden_counts["c1_indeterminable"]]
