@@ -430,9 +430,14 @@ def main():
         except Exception:
             pass
         bytes_per_launch = n * (19 * 8 + 1 + 4 + 8)
+        traffic = None
+        try:  # DRAM bytes of one launch from the committed ncu capture of this workload (not measured in this run)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[name]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-            "traffic": None,
+            "traffic": traffic,
             "peak_source": "measured in this run by rqcd_measure_fp64_peak: dependent-free DMUL+DADD chains (the "
                            "ceiling of the -fmad=false exact mode); dfma_peak is the FMA-counted figure",
             "dfma_peak": peaks["dfma_flops"] / 1e12, "frac_of_dfma_peak": achieved / (peaks["dfma_flops"] / 1e12),
