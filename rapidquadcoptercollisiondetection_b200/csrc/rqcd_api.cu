@@ -37,8 +37,8 @@ struct DevBuf {
 struct rqcd_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // host-pointer calls: copies overlap the kernel chunk by chunk
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done = nullptr, ev_start = nullptr;
+  cudaStream_t h2d_stream = nullptr;                         // host-pointer calls: input streams in beside the kernel
+  cudaEvent_t ev_in = nullptr, ev_start = nullptr;
   long long chunk_override = 0;                              // RQCD_HOST_CHUNK: candidates per chunk (0 = automatic)
   cudaDeviceProp prop;
   // obstacle set
@@ -172,7 +172,7 @@ struct CheckCall {
   }
 };
 
-int run_check(rqcd_ctx* ctx, CheckCall& cc, bool accumulate = false) {
+int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   const bool moving = !cc.pairwise && ctx->any_moving;
   CheckParams& p = cc.p;
   p.obs_blob = ctx->obs_blob.p;
@@ -196,7 +196,7 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc, bool accumulate = false) {
   int st = ensure_partials(ctx, (int)grid);
   if (st != RQCD_OK) return st;
   p.partials = ctx->d_partials;
-  RQCD_CU(launch_check(p, cc.mode, moving, cc.pairwise, (int)grid, ctx->stream, ctx->d_summary, accumulate));
+  RQCD_CU(launch_check(p, cc.mode, moving, cc.pairwise, (int)grid, ctx->stream, ctx->d_summary));
   ctx->launches += 2;  // k_check + k_finalize
   ctx->summary_valid = true;
   return RQCD_OK;
@@ -309,8 +309,8 @@ int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long lo
   };
   const long long first_end = chunk < n ? chunk : n;
   RQCD_CU(copy_chunk(0, 0, first_end));
-  RQCD_CU(cudaEventRecord(ctx->ev_in[0], hs));
-  RQCD_CU(cudaStreamWaitEvent(cs, ctx->ev_in[0], 0));
+  RQCD_CU(cudaEventRecord(ctx->ev_in, hs));
+  RQCD_CU(cudaStreamWaitEvent(cs, ctx->ev_in, 0));
   cc.p.progress = ctx->d_stream;
   cc.p.stream_error = ctx->d_stream + 1;
   int st = run_check(ctx, cc);
@@ -389,9 +389,7 @@ int rqcd_create(rqcd_ctx** out, int device) {
   DeviceGuard g(device);
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
-  for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counter, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_summary, sizeof(DevSummary));
@@ -427,8 +425,7 @@ void rqcd_destroy(rqcd_ctx* ctx) {
   if (ctx->h_stream) cudaFreeHost(ctx->h_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
-  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
-  for (cudaEvent_t ev : {ctx->ev_in[0], ctx->ev_in[1], ctx->ev_done, ctx->ev_start})
+  for (cudaEvent_t ev : {ctx->ev_in, ctx->ev_start})
     if (ev) cudaEventDestroy(ev);
   delete ctx;
 }

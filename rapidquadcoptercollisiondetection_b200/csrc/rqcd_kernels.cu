@@ -27,9 +27,7 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef RQCD_LOCKSTEP
 #define RQCD_LOCKSTEP 1
 #endif
-#ifndef RQCD_SYNC_EVERY
-#define RQCD_SYNC_EVERY 1
-#endif
+
 
 // ---- TMA bulk copy global -> shared (1-D), completion on an mbarrier ---------------------------------
 RQCD_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,14 +154,13 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   const unsigned lt_mask = (1u << lane) - 1u;
 
   int n_have = 0;
-  unsigned trip = 0;
   unsigned long long avail = 0;  // candidates known to have arrived (streaming input)
   for (;;) {
 #if RQCD_LOCKSTEP == 1
     // ---- CTA barrier once per trip: the warps of a CTA walk the (larger than the 32 KB instruction cache) loop
     // body in step, so an instruction line fetched from L2 serves all of them; the same instruction counts the
     // CTA's idle lanes for the work-queue trigger
-    if ((trip++ % RQCD_SYNC_EVERY) == 0) n_have = __syncthreads_count(have);
+    n_have = __syncthreads_count(have);
     const bool fetch_now = (kThreads - n_have >= p.refill_min * (kThreads / 32)) || n_have == 0;
 #else
     const bool fetch_now = true;
@@ -416,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   }
 }
 
-__global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int nparts, DevSummary* out, int accumulate) {
+__global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int nparts, DevSummary* out) {
   __shared__ unsigned long long cnt[8];
   __shared__ double scost[256];
   __shared__ long long sidx[256];
@@ -447,16 +444,6 @@ __global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int
         bc = scost[j];
         bi = sidx[j];
       }
-    if (accumulate) {  // a later chunk of the same call: chunks run in stream order, so this stays deterministic
-      for (int v = 0; v < 4; v++) {
-        cnt[v] += out->traj[v];
-        cnt[4 + v] += out->pair[v];
-      }
-      if (better(out->best_cost, out->best_index, bc, bi)) {
-        bc = out->best_cost;
-        bi = out->best_index;
-      }
-    }
     for (int v = 0; v < 4; v++) {
       out->traj[v] = cnt[v];
       out->pair[v] = cnt[4 + v];
@@ -759,7 +746,7 @@ int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, size_t smem) {
 }
 
 cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
-                         DevSummary* d_summary, bool accumulate) {
+                         DevSummary* d_summary) {
   const size_t smem = check_smem_bytes(pairwise ? 0 : p.mp, pairwise ? 0 : p.stride, moving);
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
@@ -771,7 +758,7 @@ cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairw
   void* args[] = {&q};
   e = cudaLaunchKernel(select_check(mode, moving, pairwise), dim3(grid), dim3(kThreads), args, smem, s);
   if (e != cudaSuccess) return e;
-  k_finalize<<<1, 256, 0, s>>>(p.partials, grid, d_summary, accumulate ? 1 : 0);
+  k_finalize<<<1, 256, 0, s>>>(p.partials, grid, d_summary);
   return cudaGetLastError();
 }
 
