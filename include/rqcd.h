@@ -153,6 +153,10 @@ typedef struct rqcd_out {
 /* flags */
 #define RQCD_F_DEVICE_PTRS 0x1u /* every data pointer in the in/out structs is a device pointer on the
                                    context's GPU; the call only enqueues work on the context's stream */
+/* Without RQCD_F_DEVICE_PTRS the data pointers are HOST pointers and the call returns when the results are in the
+ * caller's buffers. Page-locked (cudaHostAlloc / cudaHostRegister) input streams in chunk by chunk beside ONE
+ * persistent launch (the copy engine advances a progress word the kernel waits on); pageable input is copied
+ * completely before the launch. */
 #define RQCD_F_EARLY_EXIT 0x2u  /* stop each trajectory at its first non-NoCollision obstacle (what the
                                    Forest driver does); default is all pairs */
 
