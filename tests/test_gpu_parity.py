@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from rapidquadcoptercollisiondetection_b200 import abi, workloads as W
-from tests.util import assert_close, assert_roots_match, obstacles_from
+from tests.util import assert_close, assert_roots_match, degenerate_case, obstacles_from
 
 pytestmark = pytest.mark.gpu
 MIN_T = 0.002
@@ -257,3 +257,20 @@ def test_reference_drivers_known_answers_at_full_size(ctx, oracle, golden_counts
     r = ctx.generate_check_pairwise(bc, sph, MIN_T)
     assert r["summary"]["traj_counts"][:3] == [golden_counts["c1_no_collision"], golden_counts["c1_collision"],
                                               golden_counts["c1_indeterminable"]]
+
+
+def test_degenerate_inputs_follow_the_reference_arithmetic(ctx, oracle):
+    """Inputs the reference neither rejects nor handles specially -- zero / tiny / huge durations, overflowing states,
+    NaN boundary conditions, points exactly on an obstacle's surface -- must take the same IEEE path on the GPU
+    (NaN compares false everywhere, `<=` counts touching as inside, tiny windows are Indeterminable)."""
+    bc, specs = degenerate_case()
+    obs = abi.make_obstacles(specs)
+    ctx.set_obstacles(obs, len(specs))
+    for min_t in (0.002, 1e-5):
+        r = ctx.generate_check(bc, min_t)
+        o = oracle.generate_check(bc, obs, len(specs), min_t, nthreads=8)
+        np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"])
+        np.testing.assert_array_equal(r["verdict"], o["verdict"])
+        assert r["summary"]["traj_counts"] == o["summary"]["traj_counts"]
+        assert r["summary"]["best_index"] == o["summary"]["best_index"]
+    assert set(np.unique(o["verdict_matrix"])) == {0, 1, 2}

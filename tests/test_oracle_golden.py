@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from rapidquadcoptercollisiondetection_b200 import abi, workloads as W
-from tests.util import obstacles_from
+from tests.util import degenerate_case, obstacles_from
 
 MIN_T = 0.002
 
@@ -146,3 +146,15 @@ def test_oracle_equals_live_reference_on_fresh_inputs(oracle, reference):
     feas_a = oracle.input_feasibility(bc)
     feas_b = reference.input_feasibility(bc)
     np.testing.assert_array_equal(feas_a, feas_b)
+
+
+def test_degenerate_inputs_oracle_equals_live_reference(oracle, reference):
+    """Zero / tiny / huge durations, overflow, NaN states, points exactly on a surface, a zero quaternion: the
+    restatement follows the unmodified reference through every NaN and inf."""
+    bc, specs = degenerate_case()
+    obs = abi.make_obstacles(specs)
+    for min_t in (0.002, 1e-5):
+        a = oracle.generate_check(bc, obs, len(specs), min_t)
+        b = reference.generate_check(bc, obs, len(specs), min_t)
+        np.testing.assert_array_equal(a["verdict_matrix"], b["verdict_matrix"])
+        assert a["summary"] == b["summary"]

@@ -75,3 +75,30 @@ def assert_roots_match(coef, roots_a, cnt_a, roots_b, cnt_b, what="", skip=()):
                     assert np.all(res_a <= 16 * res_b + floor), \
                         f"{what}: root {k} at {bad[:5]} is a worse root than the reference's: {res_a[:5]} vs {res_b[:5]}"
     assert outliers <= max(1, 1e-4 * n), f"{what}: {outliers} ill-conditioned outliers in {n} cases"
+
+
+def degenerate_case():
+    """Inputs the reference neither rejects nor handles specially (it returns whatever IEEE arithmetic gives)."""
+    n = 4096
+    bc = W.synth_bc(71, 0, n)
+    rng = np.random.default_rng(71)
+    bc[abi.BC_TF, 0:64] = 0.0                       # division by zero in the closed forms -> NaN coefficients
+    bc[abi.BC_TF, 64:128] = 1e-4                    # whole window below minTimeSection
+    bc[abi.BC_TF, 128:192] = 1e3                    # long flights: deep recursions
+    bc[abi.BC_PF:abi.BC_PF + 3, 192:256] = 1e300    # overflow to inf in the coefficients
+    bc[abi.BC_V0, 256:320] = np.nan                 # NaN initial state
+    bc[abi.BC_A0:abi.BC_A0 + 3, 320:384] = 0.0      # start exactly on a sphere's surface, at rest:
+    bc[abi.BC_V0:abi.BC_V0 + 3, 320:384] = 0.0
+    bc[abi.BC_P0, 320:384] = 1.0                    #   |p0 - c| == r for the unit sphere at the origin
+    bc[abi.BC_P0 + 1:abi.BC_P0 + 3, 320:384] = 0.0
+    bc[:, 384:448] = 0.0                            # everything zero incl. Tf
+    bc[abi.BC_TF, 448:512] = rng.uniform(1e-3, 3e-3, 64)  # windows around minTimeSection itself
+    specs = [
+        {"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 1.0},
+        {"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 1e6},   # everything starts inside
+        {"type": "sphere", "center": [1e9, 0.0, 0.0], "radius": 1e-3},  # nothing comes near
+        {"type": "prism", "center": [0.5, 0.0, 0.0], "side": [1.0, 1.0, 1.0], "quat": [1.0, 0, 0, 0]},  # p0 = (1,0,0) on a face
+        {"type": "prism", "center": [0.0, 0.0, 2.0], "side": [1e-6, 8.0, 8.0], "quat": [0.7071067811865476, 0, 0.7071067811865476, 0]},
+        {"type": "prism", "center": [0.0, 0.0, 0.0], "side": [0.3, 0.2, 0.1], "quat": [0.0, 0.0, 0.0, 0.0]},  # zero quaternion
+    ]
+    return bc, specs
