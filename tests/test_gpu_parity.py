@@ -274,3 +274,60 @@ def test_degenerate_inputs_follow_the_reference_arithmetic(ctx, oracle):
         assert r["summary"]["traj_counts"] == o["summary"]["traj_counts"]
         assert r["summary"]["best_index"] == o["summary"]["best_index"]
     assert set(np.unique(o["verdict_matrix"])) == {0, 1, 2}
+
+
+def test_device_pointer_mode_equals_host_mode(ctx, vectors):
+    """RQCD_F_DEVICE_PTRS: every entry point reads and writes device memory on the context's stream; results equal
+    the host-pointer calls. (torch is used only to own the device buffers.)"""
+    import ctypes as C
+
+    import torch
+    dev = torch.device("cuda", 0)
+    lib, h = ctx.lib, ctx.h
+    obs, m = obstacles_from(vectors, "ck_obs_")
+    ctx.set_obstacles(obs, m)
+    coeffs, t_end, t_start, cost = (vectors[k] for k in ("ck_coeffs", "ck_t_end", "ck_t_start", "ck_cost"))
+    n = coeffs.shape[1]
+    host = ctx.check(coeffs, t_end, MIN_T, t_start=t_start, cost=cost)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
+         dict(coeffs=coeffs, t_end=t_end, t_start=t_start, cost=cost).items()}
+    ver = torch.zeros(n, dtype=torch.uint8, device=dev)
+    first = torch.zeros(n, dtype=torch.int32, device=dev)
+    mtx = torch.zeros((n, m), dtype=torch.uint8, device=dev)
+    summ = abi.Summary()
+    inp = abi.CoeffSoa(d["coeffs"].data_ptr(), n, d["t_start"].data_ptr(), d["t_end"].data_ptr())
+    out = abi.Out(verdict=ver.data_ptr(), first_obstacle=first.data_ptr(), verdict_matrix=mtx.data_ptr(), summary=C.pointer(summ))
+    torch.cuda.synchronize()
+    assert lib.rqcd_check(h, C.byref(inp), C.c_void_p(d["cost"].data_ptr()), n, MIN_T, abi.F_DEVICE_PTRS, 0, C.byref(out)) == abi.OK
+    np.testing.assert_array_equal(mtx.cpu().numpy(), host["verdict_matrix"])
+    np.testing.assert_array_equal(first.cpu().numpy(), host["first_obstacle"])
+    assert summ.as_dict() == host["summary"]
+
+    # planes + input feasibility + generate, device mode
+    bc = W.synth_bc(91, 0, 10_000)
+    planes = np.array([[0, 0, -1.0, 0, 0, 1.0], [2.0, 0, 0, -1.0, 0.2, 0]])
+    pv_host, pm_host = ctx.generate_check_planes(bc, planes)
+    feas_host = ctx.input_feasibility(bc)
+    gen_host = ctx.generate(bc)
+    d_bc = torch.from_numpy(bc).to(dev)
+    nb = bc.shape[1]
+    pv = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    pm = torch.zeros((nb, 2), dtype=torch.uint8, device=dev)
+    fe = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    co = torch.zeros(nb, dtype=torch.float64, device=dev)
+    cf = torch.zeros((18, nb), dtype=torch.float64, device=dev)
+    binp = abi.BcSoa(d_bc.data_ptr(), nb, abi.GOAL_ALL, 0)
+    torch.cuda.synchronize()
+    assert lib.rqcd_generate_check_planes(h, C.byref(binp), nb, planes.ctypes.data_as(C.c_void_p), 2, abi.F_DEVICE_PTRS,
+                                          C.c_void_p(pv.data_ptr()), C.c_void_p(pm.data_ptr())) == abi.OK
+    g = np.array([0.0, 0.0, -9.81])
+    assert lib.rqcd_check_input_feasibility(h, C.byref(binp), nb, g.ctypes.data_as(C.c_void_p), 5.0, 30.0, 20.0, 0.002, None,
+                                            abi.F_DEVICE_PTRS, C.c_void_p(fe.data_ptr())) == abi.OK
+    gout = abi.Out(cost=co.data_ptr(), coeffs=cf.data_ptr(), coeff_stride=nb)
+    assert lib.rqcd_generate(h, C.byref(binp), nb, abi.F_DEVICE_PTRS, C.byref(gout)) == abi.OK
+    ctx.synchronize()
+    np.testing.assert_array_equal(pm.cpu().numpy(), pm_host)
+    np.testing.assert_array_equal(pv.cpu().numpy(), pv_host)
+    np.testing.assert_array_equal(fe.cpu().numpy(), feas_host)
+    np.testing.assert_array_equal(co.cpu().numpy(), gen_host["cost"])
+    np.testing.assert_array_equal(cf.cpu().numpy(), gen_host["coeffs"])
