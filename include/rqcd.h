@@ -242,6 +242,37 @@ int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n
                            double fmax, double wmax, double min_time_section, const int64_t* group, uint32_t flags,
                            uint8_t* result);
 
+/* ---- the planner's candidate loop ----------------------------------------------
+ * The reference ships the stages but not the loop that chains them (its docs describe one, StoppingTrajFinder::
+ * GetBestTraj, whose sources are not in the tree): generate every candidate, drop those that cost too much, that are
+ * not input feasible, that cross a plane boundary or that hit an obstacle, and return the cheapest survivor. This
+ * entry point is that chain on the device; each stage is the corresponding call above, so per stage the results are
+ * the reference's. stage[i] (may be NULL) says where candidate i stopped. */
+typedef enum rqcd_plan_stage {
+  RQCD_PLAN_FEASIBLE = 0,        /* survived every stage: candidates for summary.best_* */
+  RQCD_PLAN_COST = 1,            /* GetCost() > max_cost (or NaN) */
+  RQCD_PLAN_INPUT = 2,           /* CheckInputFeasibility != InputFeasible */
+  RQCD_PLAN_BOUNDARY = 3,        /* CollisionCheck(Boundary) == Collision for some plane */
+  RQCD_PLAN_COLLISION = 4,       /* CollisionCheck(obstacle) == Collision for some obstacle */
+  RQCD_PLAN_INDETERMINABLE = 5   /* ... == CollisionIndeterminable */
+} rqcd_plan_stage;
+
+typedef struct rqcd_plan_params {
+  double max_cost;          /* +inf: keep all */
+  int32_t check_input;      /* 0: skip the input-feasibility stage */
+  double gravity[3];
+  double fmin, fmax, wmax;  /* CheckInputFeasibility(fminAllowed, fmaxAllowed, wmaxAllowed, .) */
+  const double* planes;     /* HOST pointer, n_planes x 6 {point, normal}; may be NULL */
+  int32_t n_planes;
+  double min_time_section;  /* for both recursive tests */
+} rqcd_plan_params;
+
+/* in: boundary conditions (host or device per flags). stage: [n] bytes (host or device per flags) or NULL.
+ * summary: HOST pointer, required; traj_counts / pair_counts cover the candidates that reached the obstacle stage,
+ * best_cost / best_index the cheapest RQCD_PLAN_FEASIBLE candidate (index_base + i, lowest index on ties). */
+int rqcd_plan_best(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const rqcd_plan_params* params, uint32_t flags,
+                   int64_t index_base, uint8_t* stage, rqcd_summary* summary);
+
 /* ---- solver unit entry points (test surface of Quartic::solveP3 / solve_quartic,
  * src/quartic.cpp:39-156). coef: 3 (cubic a,b,c) or 4 (quartic a,b,c,d) rows of n doubles, row stride n.
  * roots: 3 or 4 rows of n doubles (row stride n); count[n]. Host or device pointers per flags. */

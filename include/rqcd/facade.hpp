@@ -246,6 +246,33 @@ class Batch {
     return res;
   }
 
+  // The planner's candidate loop (rqcd_plan_best): drop candidates that cost more than maxCost, that are not input
+  // feasible, that cross one of `planes` or that hit an obstacle; summary.best_* is the cheapest survivor.
+  struct Plan {
+    std::vector<uint8_t> stage;  // rqcd_plan_stage per candidate
+    rqcd_summary summary;
+  };
+  Plan PlanBest(const double* bc, int64_t n, double minTimeSection, double maxCost, const CommonMath::Vec3& gravity,
+                double fminAllowed, double fmaxAllowed, double wmaxAllowed,
+                const std::vector<CommonMath::Boundary>& planes = {}, uint32_t goalMask = RQCD_GOAL_ALL) {
+    Plan r;
+    r.stage.resize(n);
+    std::vector<double> pl;
+    for (auto& b : planes)
+      for (double v : {b.point.x, b.point.y, b.point.z, b.normal.x, b.normal.y, b.normal.z}) pl.push_back(v);
+    rqcd_plan_params prm = {};
+    prm.max_cost = maxCost;
+    prm.check_input = 1;
+    prm.gravity[0] = gravity.x, prm.gravity[1] = gravity.y, prm.gravity[2] = gravity.z;
+    prm.fmin = fminAllowed, prm.fmax = fmaxAllowed, prm.wmax = wmaxAllowed;
+    prm.planes = pl.empty() ? nullptr : pl.data();
+    prm.n_planes = (int32_t)planes.size();
+    prm.min_time_section = minTimeSection;
+    rqcd_bc_soa in = {bc, n, goalMask, 0};
+    ctx_.check(rqcd_plan_best(ctx_.get(), &in, n, &prm, 0, 0, r.stage.data(), &r.summary), true);
+    return r;
+  }
+
   int32_t NumObstacles() const { return m_; }
 
  private:

@@ -79,6 +79,20 @@ class Summary(C.Structure):
         }
 
 
+class PlanParams(C.Structure):
+    _fields_ = [
+        ("max_cost", C.c_double),
+        ("check_input", C.c_int32),
+        ("gravity", C.c_double * 3),
+        ("fmin", C.c_double),
+        ("fmax", C.c_double),
+        ("wmax", C.c_double),
+        ("planes", C.c_void_p),
+        ("n_planes", C.c_int32),
+        ("min_time_section", C.c_double),
+    ]
+
+
 class Out(C.Structure):
     _fields_ = [
         ("verdict", C.c_void_p),
@@ -119,6 +133,8 @@ SYMBOLS = {
         C.c_int,
         [_VP, C.POINTER(BcSoa), C.c_int64, _VP, C.c_double, C.c_double, C.c_double, C.c_double, _VP, C.c_uint32, _VP],
     ),
+    "rqcd_plan_best": (C.c_int, [_VP, C.POINTER(BcSoa), C.c_int64, C.POINTER(PlanParams), C.c_uint32, C.c_int64, _VP,
+                                 C.POINTER(Summary)]),
     "rqcd_solve_cubic": (C.c_int, [_VP, _VP, C.c_int64, C.c_uint32, _VP, _VP]),
     "rqcd_solve_quartic": (C.c_int, [_VP, _VP, C.c_int64, C.c_uint32, _VP, _VP]),
     "rqcd_merge_summaries": (C.c_int, [C.POINTER(Summary), C.c_int32, C.POINTER(Summary)]),

@@ -201,6 +201,29 @@ class Context:
                                                   _ptr(res)))
         return res
 
+    def plan_best(self, bc, min_t, max_cost=float("inf"), input_limits=(5.0, 30.0, 20.0), gravity=(0.0, 0.0, -9.81),
+                  planes=None, goal_mask=abi.GOAL_ALL, index_base=0):
+        """rqcd_plan_best: cost prune -> input feasibility -> plane boundaries -> obstacles -> cheapest survivor."""
+        bc = np.ascontiguousarray(bc, dtype=np.float64)
+        n = bc.shape[1]
+        prm = abi.PlanParams()
+        prm.max_cost = max_cost
+        prm.check_input = 1 if input_limits is not None else 0
+        prm.gravity[:] = [float(x) for x in gravity]
+        if input_limits is not None:
+            prm.fmin, prm.fmax, prm.wmax = (float(x) for x in input_limits)
+        if planes is not None:
+            planes = np.ascontiguousarray(planes, dtype=np.float64).reshape(-1, 6)
+            prm.planes = planes.ctypes.data
+            prm.n_planes = planes.shape[0]
+        prm.min_time_section = min_t
+        stage = np.full(n, 255, dtype=np.uint8)
+        summ = abi.Summary()
+        inp = abi.BcSoa(_ptr(bc), n, goal_mask, 0)
+        st = self._chk(self.lib.rqcd_plan_best(self.h, C.byref(inp), n, C.byref(prm), 0, index_base, _ptr(stage), C.byref(summ)),
+                       allow=(abi.ERR_DEPTH_CAP,))
+        return {"stage": stage, "summary": summ.as_dict(), "status": st}
+
     def solve_cubic(self, coef):
         coef = np.ascontiguousarray(coef, dtype=np.float64)
         n = coef.shape[1]

@@ -799,6 +799,86 @@ int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n
   return RQCD_OK;
 }
 
+int rqcd_plan_best(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const rqcd_plan_params* prm, uint32_t flags,
+                   int64_t index_base, uint8_t* stage, rqcd_summary* summary) {
+  if (!ctx || !in || !prm || !summary || n < 0 || (n > 0 && !in->data) || in->stride < n || bad_min_t(prm->min_time_section) ||
+      prm->n_planes < 0 || (prm->n_planes > 0 && !prm->planes))
+    return RQCD_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  const bool dev = flags & RQCD_F_DEVICE_PTRS;
+  cudaStream_t s = ctx->stream;
+  // inputs on the device
+  const double* d_bc = in->data;
+  long long stride = in->stride;
+  if (!dev) {
+    RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
+    RQCD_CU(rows_h2d(ctx->s_in.p, in->data, in->stride, n, RQCD_BC_ROWS, s));
+    d_bc = (const double*)ctx->s_in.p;
+    stride = n;
+  }
+  // scratch: cost, feasibility, plane hits, stage, verdict
+  RQCD_CU(ensure(ctx->s_cost, (size_t)(n > 0 ? n : 1) * 8));
+  RQCD_CU(ensure(ctx->s_aux, (size_t)(n > 0 ? n : 1) * 4));
+  RQCD_CU(ensure(ctx->s_verdict, (size_t)(n > 0 ? n : 1)));
+  double* d_cost = (double*)ctx->s_cost.p;
+  uint8_t* d_feas = (uint8_t*)ctx->s_aux.p;
+  uint8_t* d_plane = d_feas + n;
+  uint8_t* d_stage_scratch = d_feas + 2 * n;
+  uint8_t* d_stage = (dev && stage) ? stage : d_stage_scratch;
+  uint8_t* d_verdict = (uint8_t*)ctx->s_verdict.p;
+  CheckParams p = {};
+  p.in = d_bc;
+  p.in_stride = stride;
+  p.goal_mask = in->goal_mask;
+  p.n = n;
+  // stage 0: Generate + GetCost
+  RQCD_CU(launch_generate(d_bc, stride, in->goal_mask, n, d_cost, nullptr, 0, s));
+  ctx->launches += n > 0;
+  // stage 1: CheckInputFeasibility
+  if (prm->check_input && n > 0) {
+    RQCD_CU(launch_feasibility(p, prm->gravity, prm->fmin, prm->fmax, prm->wmax, prm->min_time_section, nullptr, nullptr,
+                               d_feas, s));
+    ctx->launches++;
+  }
+  // stage 2: plane boundaries
+  if (prm->n_planes > 0) {
+    std::vector<double> prep((size_t)prm->n_planes * 6);
+    for (int k = 0; k < prm->n_planes; k++) {
+      const double* q = prm->planes + 6 * k;
+      for (int i = 0; i < 6; i++)
+        if (!std::isfinite(q[i])) return RQCD_ERR_INVALID_ARG;
+      const double nn = (double)(float)std::sqrt(q[3] * q[3] + q[4] * q[4] + q[5] * q[5]);
+      for (int i = 0; i < 3; i++) prep[6 * k + i] = q[i], prep[6 * k + 3 + i] = q[3 + i] / nn;
+    }
+    RQCD_CU(ensure(ctx->s_planes, prep.size() * 8));
+    RQCD_CU(cudaStreamSynchronize(s));
+    RQCD_CU(cudaMemcpy(ctx->s_planes.p, prep.data(), prep.size() * 8, cudaMemcpyHostToDevice));
+    if (n > 0) {
+      RQCD_CU(launch_planes(p, MODE_BC, (const double*)ctx->s_planes.p, prm->n_planes, d_plane, nullptr, s));
+      ctx->launches++;
+    }
+  }
+  RQCD_CU(launch_plan_mask(n, d_cost, prm->max_cost, prm->check_input ? d_feas : nullptr,
+                           prm->n_planes > 0 ? d_plane : nullptr, d_stage, s));
+  ctx->launches += n > 0;
+  // stage 3: obstacles, only for the survivors; argmin cost among those that stay collision free
+  CheckCall cc;
+  cc.mode = MODE_BC;
+  cc.p = p;
+  cc.p.index_base = index_base;
+  cc.p.min_t = prm->min_time_section;
+  cc.p.skip = d_stage;
+  cc.p.verdict = d_verdict;
+  cc.p.early_exit = 1;
+  if (n > 0) RQCD_CU(cudaMemsetAsync(d_verdict, 0, (size_t)n, s));
+  int st = run_check(ctx, cc);
+  if (st != RQCD_OK) return st;
+  RQCD_CU(launch_plan_stage(n, d_verdict, d_stage, s));
+  ctx->launches += n > 0;
+  if (stage && !(dev) && n > 0) RQCD_CU(cudaMemcpyAsync(stage, d_stage, (size_t)n, cudaMemcpyDeviceToHost, s));
+  return fetch_summary(ctx, summary);
+}
+
 static int solve_common(rqcd_ctx* ctx, bool quartic, const double* coef, int64_t n, uint32_t flags, double* roots,
                         int32_t* count) {
   if (!ctx || n < 0 || (n > 0 && (!coef || !roots || !count))) return RQCD_ERR_INVALID_ARG;

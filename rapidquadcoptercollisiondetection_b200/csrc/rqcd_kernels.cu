@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         }
         if (!have) {
           const long long i = (long long)b + __popc(need & lt_mask);
-          if (i < p.n && arrived) {
+          const bool rejected = (i < p.n) && arrived && p.skip && p.skip[i] != 0;  // planner: dropped by an earlier stage
+          if (i < p.n && arrived && !rejected) {
             idx = i;
             double t0, t1, cost;
             load_trajectory<MODE>(p, i, c, t0, t1, cost);
@@ -237,8 +238,9 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
     };
     if (fetch_now) fetch_work();
 #if RQCD_LOCKSTEP == 1
-    // nothing anywhere in the CTA and the fetch above brought nothing: every warp has seen the queue run dry
-    if (n_have == 0 && __syncthreads_count(have) == 0) break;
+    // nothing anywhere in the CTA, the fetch above brought nothing and every warp has seen the queue run dry (a
+    // fetch can also come back empty-handed when the planner's earlier stages rejected all it took)
+    if (n_have == 0 && __syncthreads_count(have || !exhausted) == 0) break;
     if (__ballot_sync(kFull, have) == 0) continue;  // this warp is done; keep meeting the CTA at the barrier
 #else
     if (exhausted && __ballot_sync(kFull, have) == 0) break;
@@ -620,6 +622,22 @@ __global__ void __launch_bounds__(128) k_feas(const CheckParams p, const FeasArg
   }
 }
 
+// ---- planner glue: stage code per candidate (rqcd_plan_stage). A non-zero stage doubles as k_check's skip mask.
+__global__ void __launch_bounds__(256) k_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas,
+                                                   const uint8_t* plane_hit, uint8_t* stage) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint8_t st = 0;
+    if (!(cost[i] <= max_cost)) st = 1;            // cost pruned (a NaN cost is pruned too)
+    else if (feas && feas[i] != 0) st = 2;         // input infeasible or indeterminable
+    else if (plane_hit && plane_hit[i] != 0) st = 3;  // a plane boundary is violated
+    stage[i] = st;
+  }
+}
+__global__ void __launch_bounds__(256) k_plan_stage(long long n, const uint8_t* verdict, uint8_t* stage) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (stage[i] == 0 && verdict[i] != 0) stage[i] = (uint8_t)(3 + verdict[i]);  // 4 collision, 5 indeterminable, 6 depth cap
+}
+
 // ---- solver unit kernels (test surface of Quartic::solveP3 / solve_quartic) ---------------------------
 __global__ void __launch_bounds__(256) k_solve(bool quartic, const double* coef, long long n, double* roots, int* count) {
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
@@ -784,6 +802,18 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
     if (e != cudaSuccess) return e;
   }
   k_feas<<<grid, 128, 0, s>>>(p, fa, group ? peaks : nullptr, result);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas, const uint8_t* plane_hit,
+                             uint8_t* stage, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_plan_mask<<<grid_for(n, 148 * 8), 256, 0, s>>>(n, cost, max_cost, feas, plane_hit, stage);
+  return cudaGetLastError();
+}
+cudaError_t launch_plan_stage(long long n, const uint8_t* verdict, uint8_t* stage, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_plan_stage<<<grid_for(n, 148 * 8), 256, 0, s>>>(n, verdict, stage);
   return cudaGetLastError();
 }
 

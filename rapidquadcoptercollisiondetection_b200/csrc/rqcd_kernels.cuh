@@ -65,6 +65,8 @@ struct CheckParams {
   // The copy engine advances *progress after each chunk; *stream_error is set if a wait times out.
   const unsigned long long* progress;
   unsigned long long* stream_error;
+  // planner: candidates with skip[i] != 0 were rejected by an earlier stage and are not checked (nor counted)
+  const uint8_t* skip;
 };
 
 size_t check_smem_bytes(int mp, int stride, bool moving);
@@ -79,6 +81,10 @@ cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, 
 // group may be null; peaks: scratch of 6*n doubles, needed when group is given
 cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], double fmin, double fmax, double wmax,
                                double min_t, const long long* group, double* peaks, uint8_t* result, cudaStream_t s);
+// planner glue (rqcd_plan_best): stage codes, see rqcd_plan_stage in rqcd.h
+cudaError_t launch_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas, const uint8_t* plane_hit,
+                             uint8_t* stage, cudaStream_t s);
+cudaError_t launch_plan_stage(long long n, const uint8_t* verdict, uint8_t* stage, cudaStream_t s);
 cudaError_t launch_generate(const double* bc, long long stride, unsigned goal_mask, long long n, double* cost,
                             double* coeffs, long long coeff_stride, cudaStream_t s);
 cudaError_t launch_solve(bool quartic, const double* coef, long long n, double* roots, int* count, cudaStream_t s);

@@ -331,3 +331,43 @@ def test_device_pointer_mode_equals_host_mode(ctx, vectors):
     np.testing.assert_array_equal(fe.cpu().numpy(), feas_host)
     np.testing.assert_array_equal(co.cpu().numpy(), gen_host["cost"])
     np.testing.assert_array_equal(cf.cpu().numpy(), gen_host["coeffs"])
+
+
+def test_planner_chain_equals_the_stages_composed(ctx, oracle):
+    """rqcd_plan_best = cost prune -> CheckInputFeasibility -> CollisionCheck(Boundary) -> CollisionCheck(obstacles)
+    -> argmin GetCost, against the same chain composed from the oracle's stage functions."""
+    n = 60_000
+    bc = W.synth_bc(81, 500, n)
+    bc[abi.BC_PF:abi.BC_PF + 3] *= 0.5     # shorter hops: more input-feasible candidates
+    specs = W.static_obstacles(82, 3, 3, extent=3.0)
+    obs = abi.make_obstacles(specs)
+    ctx.set_obstacles(obs, len(specs))
+    planes = np.array([[0, 0, -1.5, 0, 0, 1.0], [0, 3.0, 0, 0, -2.0, 0]])
+    g = oracle.generate(bc)
+    max_cost = float(np.percentile(g["cost"], 80))
+    for use_input, use_planes in ((True, True), (False, True), (True, False), (False, False)):
+        r = ctx.plan_best(bc, MIN_T, max_cost=max_cost, input_limits=(5.0, 30.0, 20.0) if use_input else None,
+                          planes=planes if use_planes else None, index_base=500)
+        want = np.zeros(n, dtype=np.uint8)
+        want[~(g["cost"] <= max_cost)] = 1
+        if use_input:
+            feas = oracle.input_feasibility(bc)
+            want[(want == 0) & (feas != 0)] = 2
+        if use_planes:
+            pv, _ = oracle.check_planes(g["coeffs"], bc[abi.BC_TF], planes)
+            want[(want == 0) & (pv != 0)] = 3
+        o = oracle.generate_check(bc, obs, len(specs), MIN_T, flags=abi.F_EARLY_EXIT, matrix=False, nthreads=8)
+        hit = (want == 0) & (o["verdict"] != 0)
+        want[hit] = 3 + o["verdict"][hit]
+        np.testing.assert_array_equal(r["stage"], want)
+        alive = np.flatnonzero(want == 0)
+        assert alive.size > 0 and len(np.unique(want)) >= (3 + use_input + use_planes)
+        best = alive[np.argmin(g["cost"][alive])]
+        assert r["summary"]["best_index"] == 500 + best
+        np.testing.assert_allclose(r["summary"]["best_cost"], g["cost"][best], rtol=1e-12)
+        reached = want == 0
+        reached |= want >= 4
+        assert sum(r["summary"]["traj_counts"]) == int(reached.sum())
+    # every candidate rejected before the obstacle stage: the kernel must come back with nothing, not hang
+    r = ctx.plan_best(bc, MIN_T, max_cost=-1.0)
+    assert (r["stage"] == 1).all() and r["summary"]["best_index"] == -1 and r["summary"]["pairs_checked"] == 0
