@@ -12,9 +12,13 @@
 //     needs 15 frames for one obstacle does not hold back its 31 neighbours -- they move on to their next
 //     obstacles. The reference's recursion is a per-lane explicit stack of pending [ts, tf] intervals.
 //   * the frame is one converged instruction stream for the whole warp (see frame() in rqcd_device.cuh): the
-//     only divergent regions are the sphere/prism arithmetic and the transcendental core of the cubic solver.
-//   * work queue: when enough lanes of a warp have finished their trajectory (ballot + popc) the warp takes
-//     that many new candidates from a global counter with one atomicAdd and the idle lanes build them.
+//     only divergent regions are the end-point inside tests (sphere vs prism) and the transcendental core of the
+//     cubic solver. No position is evaluated twice: X(ts), X(tf) travel with the interval (shared-memory rows).
+//   * CTA lockstep: one __syncthreads_count per trip keeps the warps of a CTA in the same part of the loop body,
+//     which is larger than the instruction cache, and counts the CTA's idle lanes.
+//   * work queue: when enough lanes of the CTA have finished their trajectory the warps take new candidates from a
+//     global counter (ballot + popc, one atomicAdd per warp) and the idle lanes build them. With host buffers the
+//     candidates may still be arriving over PCIe: a warp then waits for the copy engine's progress word.
 //   * per-CTA partial verdict counts / best candidate, reduced in block order by k_finalize (deterministic).
 #include "rqcd_device.cuh"
 #include "rqcd_kernels.cuh"
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   unsigned long long* wcnt = reinterpret_cast<unsigned long long*>(oflags + mp);  // [kWarps][8]
   double* bcost = reinterpret_cast<double*>(wcnt + kWarps * 8);                   // [kThreads]
   long long* bidx = reinterpret_cast<long long*>(bcost + kThreads);               // [kThreads]
-  double* slot = reinterpret_cast<double*>(bidx + kThreads);                      // [kSlotRows][kThreads], see SlotRow
+  double* slot = reinterpret_cast<double*>(bidx + kThreads);                      // [kSlotRows][kThreads]: EndPoints rows
   double* base = slot + kSlotRows * kThreads;                                     // MOVING: [18][kThreads]
   __shared__ __align__(8) uint64_t mbar;
   volatile double traj_const[kTrajRows];
@@ -166,9 +170,8 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
     const bool fetch_now = true;
 #endif
     // ---- work queue: idle lanes take new candidates
-    auto fetch_work = [&]() {
     const unsigned need = __ballot_sync(kFull, !have);
-    if (need != 0 && !exhausted) {
+    if (need != 0 && !exhausted && fetch_now) {
       const int cnt = __popc(need);
       if (RQCD_LOCKSTEP || cnt >= p.refill_min || need == kFull) {
         unsigned long long b = 0;
@@ -235,8 +238,6 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         }
       }
     }
-    };
-    if (fetch_now) fetch_work();
 #if RQCD_LOCKSTEP == 1
     // nothing anywhere in the CTA, the fetch above brought nothing and every warp has seen the queue run dry (a
     // fetch can also come back empty-handed when the planner's earlier stages rejected all it took)
