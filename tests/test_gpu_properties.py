@@ -106,3 +106,46 @@ def test_pairwise_equals_one_obstacle_sets(ctx, oracle):
         ctx.set_obstacles(abi.make_obstacles([{"type": "sphere", "center": sph[:3, i].tolist(), "radius": float(sph[3, i])}]), 1)
         one = ctx.generate_check(bc[:, i:i + 1].copy(), MIN_T)
         assert one["verdict"][0] == r["verdict"][i]
+
+
+def test_moving_set_sample_of_c4_against_oracle(ctx, oracle):
+    """BASELINE config 4 (moving, non-rotating obstacles): 2^16 primitives x 32 moving obstacles = 2.1e6 pairs."""
+    n = 1 << 16
+    specs = W.moving_obstacles(4, 32, lambda b: ctx.generate(b)["coeffs"])
+    obs = abi.make_obstacles(specs)
+    ctx.set_obstacles(obs, 32)
+    bc = W.synth_bc(3, 0, n)
+    r = ctx.generate_check(bc, MIN_T)
+    o = oracle.generate_check(bc, obs, 32, MIN_T, nthreads=16)
+    np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"])
+    np.testing.assert_array_equal(r["first_obstacle"], o["first_obstacle"])
+    assert r["summary"] == {**o["summary"], "best_cost": r["summary"]["best_cost"]}
+    assert (o["verdict_matrix"] == 1).any() and (o["verdict_matrix"] == 2).any()
+
+
+def test_large_table_sample_of_c5_against_oracle(ctx, oracle):
+    """BASELINE config 5's obstacle set (128 spheres + 128 prisms: a 51 KB table per CTA): 2^14 primitives taken from
+    the middle of the 2^26 index space x 256 obstacles = 4.2e6 pairs."""
+    n = 1 << 14
+    specs = W.static_obstacles(6, 128, 128)
+    obs = abi.make_obstacles(specs)
+    ctx.set_obstacles(obs, 256)
+    base = (1 << 25) + 12345
+    bc = W.synth_bc(5, base, n)
+    r = ctx.generate_check(bc, MIN_T, index_base=base)
+    o = oracle.generate_check(bc, obs, 256, MIN_T, index_base=base, nthreads=16)
+    np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"])
+    np.testing.assert_array_equal(r["verdict"], o["verdict"])
+    assert r["summary"]["pair_counts"] == o["summary"]["pair_counts"]
+    assert r["summary"]["best_index"] == o["summary"]["best_index"]
+
+
+def test_device_synth_equals_host_synth(ctx):
+    """rqcd_synth_bc (device) and workloads.synth_bc (numpy) are the same counter-based generator, so any candidate of
+    the 2^26-candidate configuration can be regenerated on the host for the oracle."""
+    import torch
+    n, base = 4096, (1 << 26) - 4096
+    d = torch.empty((abi.BC_ROWS, n), dtype=torch.float64, device="cuda")
+    ctx.synth_bc(5, base, n, d.data_ptr(), n)
+    ctx.synchronize()
+    np.testing.assert_array_equal(d.cpu().numpy(), W.synth_bc(5, base, n))
