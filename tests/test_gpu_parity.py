@@ -371,3 +371,22 @@ def test_planner_chain_equals_the_stages_composed(ctx, oracle):
     # every candidate rejected before the obstacle stage: the kernel must come back with nothing, not hang
     r = ctx.plan_best(bc, MIN_T, max_cost=-1.0)
     assert (r["stage"] == 1).all() and r["summary"]["best_index"] == -1 and r["summary"]["pairs_checked"] == 0
+
+
+def test_obstacle_table_limits(ctx, oracle):
+    """The prepared table must fit one CTA's shared memory next to the per-thread rows: ~700 static obstacles still
+    run (one CTA per SM), a set that cannot fit is refused with RQCD_ERR_UNSUPPORTED -- never truncated."""
+    from rapidquadcoptercollisiondetection_b200.api import RqcdError
+    specs = W.static_obstacles(15, 350, 350)
+    obs = abi.make_obstacles(specs)
+    ctx.set_obstacles(obs, 700)
+    bc = W.synth_bc(16, 0, 2000)
+    r = ctx.generate_check(bc, MIN_T)
+    o = oracle.generate_check(bc, obs, 700, MIN_T, nthreads=16)
+    np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"])
+    assert r["summary"]["pair_counts"] == o["summary"]["pair_counts"]
+    big = W.static_obstacles(17, 1500, 1500)
+    with pytest.raises(RqcdError) as e:
+        ctx.set_obstacles(abi.make_obstacles(big), 3000)
+    assert e.value.status == abi.ERR_UNSUPPORTED
+    assert ctx.num_obstacles() == 700  # the previous set stays in place
