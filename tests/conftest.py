@@ -14,6 +14,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build them once, like __graft_entry__.build()
+    lib = os.path.join(ROOT, "rapidquadcoptercollisiondetection_b200", "librqcd.so")
+    orc = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _have_gpu() -> bool:
