@@ -13,7 +13,9 @@
 //     obstacles. The reference's recursion is a per-lane explicit stack of pending [ts, tf] intervals.
 //   * the frame is one converged instruction stream for the whole warp (see frame() in rqcd_device.cuh): the
 //     only divergent regions are the end-point inside tests (sphere vs prism) and the transcendental core of the
-//     cubic solver. No position is evaluated twice: X(ts), X(tf) travel with the interval (shared-memory rows).
+//     cubic solver. The only position a frame evaluates is X(mid): the plane-side tests at the critical times and
+//     at the interval's ends are the sign of a scalar quintic (5 FMAs each) with a certified error margin and a
+//     literal fallback, so an interval is just [ts, tf].
 //   * CTA lockstep: one __syncthreads_count per trip keeps the warps of a CTA in the same part of the loop body,
 //     which is larger than the instruction cache, and counts the CTA's idle lanes.
 //   * work queue: when enough lanes of the CTA have finished their trajectory the warps take new candidates from a
@@ -61,10 +63,9 @@ RQCD_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// Per-trajectory constants (window, cost, X(t_start), X(t_end)) are read once per obstacle: they live in a
-// volatile per-thread local array (L1-resident), not in registers and not in shared memory, which is kept for the
-// obstacle table and the frame's rows so that two CTAs fit next to a 256-obstacle table.
-enum TrajRow { SLOT_T0 = 0, SLOT_T1, SLOT_COST, SLOT_X0, SLOT_X1 = SLOT_X0 + 3, kTrajRows = SLOT_X1 + 3 };
+// Per-trajectory constants (window, cost) are read once per obstacle: they live in a volatile per-thread local
+// array (L1-resident), not in registers.
+enum TrajRow { SLOT_T0 = 0, SLOT_T1, SLOT_COST, kTrajRows };
 constexpr int kSlotRows = EndPoints::kRows;  // per-thread shared-memory rows
 
 RQCD_DEV bool better(double ca, long long ia, double cb, long long ib) {
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   ends.set_xf(v3(0, 0, 0));
   int k = 0, verdict = 0, first = -1, sp = 0;
   unsigned pair_hits = 0, depth_cap_hits = 0;  // this trajectory's pairs: Collision | Indeterminable << 16; verdict 3
-  double2 stack[kMaxDepth][4];  // {ts, lo_tf}, {Xs.x, Xs.y}, {Xs.z, lo_x.x}, {lo_x.y, lo_x.z}
+  double2 stack[kMaxDepth];  // parked low children {ts, lo_tf}
   LaneSphere sph;
   sph.cx = sph.cy = sph.cz = sph.r = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -218,10 +219,10 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
 #pragma unroll
               for (int j = 0; j < 18; j++) base[j * kThreads + tid] = c[j];
             } else {
-              // X(t_start), X(t_end) of the trajectory: the same for every obstacle, evaluated once
-              const V3 a = traj_value(c, t0), e = traj_value(c, t1);
-              RQCD_SLOT(SLOT_X0 + 0) = a.x, RQCD_SLOT(SLOT_X0 + 1) = a.y, RQCD_SLOT(SLOT_X0 + 2) = a.z;
-              RQCD_SLOT(SLOT_X1 + 0) = e.x, RQCD_SLOT(SLOT_X1 + 1) = e.y, RQCD_SLOT(SLOT_X1 + 2) = e.z;
+              // X(t_start), X(t_end) of the trajectory and the side filter's bound: the same for every obstacle
+              ends.set_xs(traj_value(c, t0));
+              ends.set_xf(traj_value(c, t1));
+              ends.set_amax(side_filter_bound(c, t0, t1));
             }
             if (PAIRWISE) {
               sph.cx = ld_in(p.spheres + i);
@@ -278,9 +279,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         }
         ends.set_xs(traj_value(c, ts));
         ends.set_xf(traj_value(c, tf));
-      } else {
-        ends.set_xs(v3(RQCD_SLOT(SLOT_X0 + 0), RQCD_SLOT(SLOT_X0 + 1), RQCD_SLOT(SLOT_X0 + 2)));
-        ends.set_xf(v3(RQCD_SLOT(SLOT_X1 + 0), RQCD_SLOT(SLOT_X1 + 1), RQCD_SLOT(SLOT_X1 + 2)));
+        ends.set_amax(side_filter_bound(c, ts, tf));
       }
     }
 
@@ -290,13 +289,13 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
       Children ch;
       int r;
       if (PAIRWISE) {
-        r = frame(c, ts, tf, ends, first_frame, sph, p.min_t, ch);
+        r = frame(c, ts, tf, ends, first_frame, in_pair, sph, p.min_t, ch);
       } else {
         TableObs o;
         const int kk = min(k, max(m - 1, 0));
         o.rec = tab + (size_t)kk * p.stride;
         o.flags = oflags[kk];
-        r = frame(c, ts, tf, ends, first_frame, o, p.min_t, ch);
+        r = frame(c, ts, tf, ends, first_frame, in_pair, o, p.min_t, ch);
       }
       first_frame = false;
       // state update, written with selects: one instruction stream for the common cases (no child; one child)
@@ -305,12 +304,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
       const bool clear = in_pair & (r == STEP_CLEAR);
       if (to_hi & ch.has_lo) {  // both children: the parent's low tail call waits until the high subtree is clear
         if (sp < kMaxDepth) {
-          const V3 Xs = ends.xs();
-          stack[sp][0] = make_double2(ts, ch.lo_tf);
-          stack[sp][1] = make_double2(Xs.x, Xs.y);
-          stack[sp][2] = make_double2(Xs.z, ch.lo_x.x);
-          stack[sp][3] = make_double2(ch.lo_x.y, ch.lo_x.z);
-          sp++;
+          stack[sp++] = make_double2(ts, ch.lo_tf);
         } else {
           pv = 3;
           in_pair = false;
@@ -318,15 +312,10 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
       }
       ts = to_hi ? ch.t_next : ts;
       tf = to_lo ? ch.t_next : tf;
-      if (to_hi) ends.set_xs(ch.x_next);
-      if (to_lo) ends.set_xf(ch.x_next);
       if (clear & (sp > 0)) {  // subtree clear: resume the innermost parked low child
-        --sp;
-        const double2 e0 = stack[sp][0], e1 = stack[sp][1], e2 = stack[sp][2], e3 = stack[sp][3];
-        ts = e0.x;
-        tf = e0.y;
-        ends.set_xs(v3(e1.x, e1.y, e2.x));
-        ends.set_xf(v3(e2.y, e3.x, e3.y));
+        const double2 e = stack[--sp];
+        ts = e.x;
+        tf = e.y;
       } else if (in_pair & !child) {  // NoCollision with nothing parked, Collision or Indeterminable: the pair is done
         pv = clear ? 0 : r;
         in_pair = false;
@@ -746,7 +735,7 @@ size_t check_smem_bytes(int mp, int stride, bool moving) {
   size_t b = (size_t)stride * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
   b += (kThreads / 32) * 8 * 8;                           // warp counters
   b += (size_t)kThreads * 16;                             // best cost / index per thread
-  b += (size_t)kThreads * 8 * EndPoints::kRows;           // X(ts), X(tf) and the frame's evaluated positions
+  b += (size_t)kThreads * 8 * EndPoints::kRows;           // X(t_start), X(t_end), side-filter bound per thread
   if (moving) b += (size_t)18 * kThreads * 8;             // the lane's own coefficients
   return b;
 }
