@@ -186,8 +186,8 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   p.work_counter = ctx->d_counter;
   const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->stride, moving);
   if (smem > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
-  RQCD_CU(check_prepare(cc.mode, moving, cc.pairwise, smem));
-  int per_sm = check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, smem);
+  RQCD_CU(check_prepare(cc.mode, moving, cc.pairwise, p.m, smem));
+  int per_sm = check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, p.m, smem);
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)ctx->prop.multiProcessorCount * per_sm;
   const long long need = (p.n + kThreads - 1) / kThreads;

@@ -109,7 +109,7 @@ RQCD_DEV void load_trajectory(const CheckParams& p, long long i, double (&c)[18]
   }
 }
 
-template <int MODE, bool MOVING, bool PAIRWISE>
+template <int MODE, bool MOVING, bool PAIRWISE, bool ENDBITS>
 __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const CheckParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kWarps = kThreads / 32;
@@ -123,6 +123,9 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   long long* bidx = reinterpret_cast<long long*>(bcost + kThreads);               // [kThreads]
   double* slot = reinterpret_cast<double*>(bidx + kThreads);                      // [kSlotRows][kThreads]: EndPoints rows
   double* base = slot + kSlotRows * kThreads;                                     // MOVING: [18][kThreads]
+  // static table: bit k of a thread's words = an end point of its trajectory is inside obstacle k (kEndBits)
+  constexpr bool kEndBits = ENDBITS && !MOVING && !PAIRWISE;
+  unsigned* inbits = reinterpret_cast<unsigned*>(base);                            // [(mp + 31) / 32][kThreads]
   __shared__ __align__(8) uint64_t mbar;
   volatile double traj_const[kTrajRows];
 #define RQCD_SLOT(row) traj_const[row]
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
             }
           }
         }
+        bool fresh = false;
         if (!have) {
           const long long i = (long long)b + __popc(need & lt_mask);
           const bool rejected = (i < p.n) && arrived && p.skip && p.skip[i] != 0;  // planner: dropped by an earlier stage
@@ -231,10 +235,37 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
               sph.r = ld_in(p.spheres + 3 * p.sphere_stride + i);
             }
             have = true;
+            fresh = true;
             in_pair = false;
             k = 0;
             verdict = 0;
             first = -1;
+          }
+        }
+        if (kEndBits) {
+          // CollisionCheck's end-point tests (CollisionChecker.cpp:73-77) for the new trajectories against the whole
+          // table, by the whole warp: lane j tests obstacles j, j + 32, ... against the end points of one new
+          // trajectory at a time (read from its owner's rows), a ballot packs 32 answers into a word for the owner.
+          unsigned todo = __ballot_sync(kFull, fresh);
+          __syncwarp();
+          while (todo) {
+            const int owner = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const double* row = slot + (tid - lane + owner);
+            const V3 Xs = v3(row[0], row[kThreads], row[2 * kThreads]);
+            const V3 Xf = v3(row[3 * kThreads], row[4 * kThreads], row[5 * kThreads]);
+            for (int k0 = 0; k0 < m; k0 += 32) {
+              const int kk = k0 + lane;
+              bool inside = false;
+              if (kk < m) {
+                TableObs o;
+                o.rec = tab + (size_t)kk * p.stride;
+                o.flags = oflags[kk];
+                inside = ends_inside(o, Xs, Xf);
+              }
+              const unsigned bits = __ballot_sync(kFull, inside);
+              if (lane == owner) inbits[(k0 >> 5) * kThreads + tid] = bits;
+            }
           }
         }
       }
@@ -252,7 +283,19 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
 
     // ---- CollisionChecker::CollisionCheck entry for the lane's next obstacle (CollisionChecker.cpp:70-80);
     // its end-point tests ride on the first frame below
-    if (have && !in_pair && k < m) {
+    if (kEndBits && have && !in_pair) {
+      // pairs whose end-point test is positive are Collisions without a section (CollisionChecker.cpp:73-77)
+      while (k < m && ((inbits[(k >> 5) * kThreads + tid] >> (k & 31)) & 1u) && !(p.early_exit && verdict != 0)) {
+        if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)1;
+        if (first < 0) {
+          verdict = 1;
+          first = k;
+        }
+        pair_hits += 1u;
+        k++;
+      }
+    }
+    if (have && !in_pair && k < m && !(kEndBits && p.early_exit && verdict != 0)) {
       ts = RQCD_SLOT(SLOT_T0);
       tf = RQCD_SLOT(SLOT_T1);
       in_pair = true;
@@ -289,13 +332,13 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
       Children ch;
       int r;
       if (PAIRWISE) {
-        r = frame(c, ts, tf, ends, first_frame, in_pair, sph, p.min_t, ch);
+        r = frame<true>(c, ts, tf, ends, first_frame, in_pair, sph, p.min_t, ch);
       } else {
         TableObs o;
         const int kk = min(k, max(m - 1, 0));
         o.rec = tab + (size_t)kk * p.stride;
         o.flags = oflags[kk];
-        r = frame(c, ts, tf, ends, first_frame, in_pair, o, p.min_t, ch);
+        r = frame<!kEndBits>(c, ts, tf, ends, first_frame, in_pair, o, p.min_t, ch);
       }
       first_frame = false;
       // state update, written with selects: one instruction stream for the common cases (no child; one child)
@@ -711,15 +754,21 @@ __global__ void __launch_bounds__(kPeakThreads) k_fp64_peak(int iters, double* s
   if (s == 123.456) sink[0] = s;
 }
 
-template <int MODE, bool MOVING, bool PAIRWISE>
+template <int MODE, bool MOVING, bool PAIRWISE, bool ENDBITS>
 const void* check_fn() {
-  return reinterpret_cast<const void*>(&k_check<MODE, MOVING, PAIRWISE>);
+  return reinterpret_cast<const void*>(&k_check<MODE, MOVING, PAIRWISE, ENDBITS>);
 }
 
-const void* select_check(int mode, bool moving, bool pairwise) {
-  if (pairwise) return check_fn<MODE_BC, false, true>();
-  if (mode == MODE_BC) return moving ? check_fn<MODE_BC, true, false>() : check_fn<MODE_BC, false, false>();
-  return moving ? check_fn<MODE_COEFF, true, false>() : check_fn<MODE_COEFF, false, false>();
+// The end-point pre-pass pays off when a trajectory meets many obstacles; a handful (Forest: 5, early exit) is
+// cheaper inside the pairs' first frames.
+bool use_endbits(bool moving, bool pairwise, int m) { return !moving && !pairwise && m >= kEndBitsMinObstacles; }
+
+const void* select_check(int mode, bool moving, bool pairwise, int m) {
+  if (pairwise) return check_fn<MODE_BC, false, true, false>();
+  if (moving) return mode == MODE_BC ? check_fn<MODE_BC, true, false, false>() : check_fn<MODE_COEFF, true, false, false>();
+  if (use_endbits(moving, pairwise, m))
+    return mode == MODE_BC ? check_fn<MODE_BC, false, false, true>() : check_fn<MODE_COEFF, false, false, true>();
+  return mode == MODE_BC ? check_fn<MODE_BC, false, false, false>() : check_fn<MODE_COEFF, false, false, false>();
 }
 
 int grid_for(long long n, int cap) {
@@ -737,17 +786,18 @@ size_t check_smem_bytes(int mp, int stride, bool moving) {
   b += (size_t)kThreads * 16;                             // best cost / index per thread
   b += (size_t)kThreads * 8 * EndPoints::kRows;           // X(t_start), X(t_end), side-filter bound per thread
   if (moving) b += (size_t)18 * kThreads * 8;             // the lane's own coefficients
+  else b += (size_t)((mp + 31) / 32) * kThreads * 4;      // end-point test bits, one per obstacle and thread
   return b;
 }
 
-cudaError_t check_prepare(int mode, bool moving, bool pairwise, size_t smem) {
-  return cudaFuncSetAttribute(select_check(mode, moving, pairwise), cudaFuncAttributeMaxDynamicSharedMemorySize,
+cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem) {
+  return cudaFuncSetAttribute(select_check(mode, moving, pairwise, m), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)smem);
 }
 
-int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, size_t smem) {
+int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, select_check(mode, moving, pairwise), kThreads, smem) !=
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, select_check(mode, moving, pairwise, m), kThreads, smem) !=
       cudaSuccess)
     return 0;
   return nb;
@@ -764,7 +814,7 @@ cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairw
     q.stride = 0;
   }
   void* args[] = {&q};
-  e = cudaLaunchKernel(select_check(mode, moving, pairwise), dim3(grid), dim3(kThreads), args, smem, s);
+  e = cudaLaunchKernel(select_check(mode, moving, pairwise, p.m), dim3(grid), dim3(kThreads), args, smem, s);
   if (e != cudaSuccess) return e;
   k_finalize<<<1, 256, 0, s>>>(p.partials, grid, d_summary);
   return cudaGetLastError();

@@ -73,8 +73,9 @@ size_t check_smem_bytes(int mp, int stride, bool moving);
 // Returns the number of kernels launched (2: check + finalize) or a negative cudaError.
 cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
                          DevSummary* d_summary);
-int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, size_t smem);
-cudaError_t check_prepare(int mode, bool moving, bool pairwise, size_t smem);  // opt in to large dynamic smem
+int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem);
+cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem);  // opt in to large dynamic smem
+constexpr int kEndBitsMinObstacles = 16;  // static tables at least this long: end-point tests as a pre-pass
 
 cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, int np, uint8_t* verdict, uint8_t* matrix,
                           cudaStream_t s);
