@@ -396,6 +396,7 @@ int rqcd_create(rqcd_ctx** out, int device) {
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_summary, sizeof(DevSummary));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stream, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_stream, (kMaxChunks + 1) * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = init_device_constants(ctx->own_stream);
   if (e != cudaSuccess) {
     rqcd_destroy(ctx);
     return RQCD_ERR_CUDA;

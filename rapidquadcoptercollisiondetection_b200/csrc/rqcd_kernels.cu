@@ -754,6 +754,13 @@ __global__ void __launch_bounds__(kPeakThreads) k_fp64_peak(int iters, double* s
   if (s == 123.456) sink[0] = s;
 }
 
+__device__ double g_rcp_const[3];
+__global__ void k_init_constants() {
+  g_rcp_const[0] = rcp_refined(3.0);
+  g_rcp_const[1] = rcp_refined(9.0);
+  g_rcp_const[2] = rcp_refined(54.0);
+}
+
 template <int MODE, bool MOVING, bool PAIRWISE, bool ENDBITS>
 const void* check_fn() {
   return reinterpret_cast<const void*>(&k_check<MODE, MOVING, PAIRWISE, ENDBITS>);
@@ -779,6 +786,18 @@ int grid_for(long long n, int cap) {
 }
 
 }  // namespace
+
+cudaError_t init_device_constants(cudaStream_t s) {
+  k_init_constants<<<1, 1, 0, s>>>();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  void* src = nullptr;
+  e = cudaGetSymbolAddress(&src, g_rcp_const);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbolAsync(kRcpConst, src, sizeof(double) * 3, 0, cudaMemcpyDeviceToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);
+}
 
 size_t check_smem_bytes(int mp, int stride, bool moving) {
   size_t b = (size_t)stride * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)

@@ -69,6 +69,8 @@ struct CheckParams {
   const uint8_t* skip;
 };
 
+// once per device, before any kernel that solves a cubic: the refined reciprocals of solveP3's constant divisors
+cudaError_t init_device_constants(cudaStream_t s);
 size_t check_smem_bytes(int mp, int stride, bool moving);
 // Returns the number of kernels launched (2: check + finalize) or a negative cudaError.
 cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
