@@ -47,6 +47,14 @@ __global__ void k(unsigned long long seed, unsigned long long* bad, unsigned lon
       q0 = x0 / y, q1 = x1 / y, q2 = x2 / y;
     }
     nbad += !same(q0, x0 / y) + !same(q1, x1 / y) + !same(q2, x2 / y);
+    {
+      SqrtGroup sg;
+      const double a0 = fabs(x0), s0 = sg(a0);
+      if (sg.ok) nbad += !same(s0, sqrt(a0));
+      SqrtGroup sh;  // negative, NaN, tiny, huge arguments must be flagged, never answered wrongly
+      const double s1 = sh(x1);
+      if (sh.ok) nbad += !same(s1, sqrt(x1));
+    }
     DivGroup d3(3.0, kRcpConst[0]), d9(9.0, kRcpConst[1]), d54(54.0, kRcpConst[2]);
     const double c0 = d3(x0), c1 = d9(x1), c2 = d54(x2);
     if (d3.ok) nbad += !same(c0, x0 / 3);
@@ -72,7 +80,7 @@ int main(int argc, char** argv) {
   for (int r = 0; r < rounds; r++) k<<<blocks, threads>>>(0x1234567ull + (unsigned long long)r * blocks * threads * 64, d, d + 1);
   cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   const double groups = (double)rounds * blocks * threads * 64;
-  printf("divcheck: %.3e divisor groups (3 shared-divisor + 3 constant-divisor quotients each), %llu differing quotients, "
+  printf("divcheck: %.3e divisor groups (3 shared-divisor + 3 constant-divisor quotients + 2 square roots each), %llu differing results, "
          "%.2f%% of the groups left the fast range  (%s)\n",
          groups, h[0], 100.0 * h[1] / groups, cudaGetErrorString(cudaGetLastError()));
   return h[0] != 0;
