@@ -1,5 +1,5 @@
-// tools/divcheck.cu -- the regrouped divisions of rqcd_device.cuh (DivGroup: shared reciprocal refinement, one range
-// vote per group) against the compiler's own FP64 division, bit for bit, over random operands of every exponent range
+// tools/divcheck.cu -- the regrouped divisions and square roots of rqcd_device.cuh (FastMath: shared reciprocal
+// refinement, accumulated range tests) against the compiler's own FP64 `/` and sqrt(), bit for bit, over random operands of every exponent range
 // plus zeros, subnormals, infinities and NaNs. Prints the number of differing quotients (must be 0).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o tools/divcheck tools/divcheck.cu && tools/divcheck [rounds]
 #include <cstdio>
@@ -39,27 +39,31 @@ __global__ void k(unsigned long long seed, unsigned long long* bad, unsigned lon
     const unsigned long long h = sm64(seed + i * 64 + it);
     const int my = (int)(h % 5), mx = (int)((h / 5) % 5);
     const double y = rnd(sm64(h ^ 1), my);
-    const double x0 = rnd(sm64(h ^ 2), mx), x1 = rnd(sm64(h ^ 3), mx), x2 = rnd(sm64(h ^ 4), (mx + 1) % 5);
-    DivGroup d(y);
-    double q0 = d(x0), q1 = d(x1), q2 = d(x2);
-    if (!d.ok) {  // per-lane here; the kernels vote per warp
-      nslow++;
-      q0 = x0 / y, q1 = x1 / y, q2 = x2 / y;
+    const double x0 = rnd(sm64(h ^ 2), mx), x2 = rnd(sm64(h ^ 4), (mx + 1) % 5);
+    double x1 = rnd(sm64(h ^ 3), mx);
+    if (it % 16 == 5) x1 = copysign(0.0, x1);  // signed zero numerators
+    {  // three quotients that share a divisor; half of them through the zero-aware form
+      FastMath fm;
+      const FastMath::Div d = fm.divisor(y);
+      const double q0 = fm.div(x0, d), q1 = fm.div_z(x1, d), q2 = (it & 1) ? fm.div(x2, d) : fm.div_z(x2, d);
+      if (fm.ok) nbad += !same(q0, x0 / y) + !same(q1, x1 / y) + !same(q2, x2 / y);
+      else nslow++;
     }
-    nbad += !same(q0, x0 / y) + !same(q1, x1 / y) + !same(q2, x2 / y);
-    {
-      SqrtGroup sg;
-      const double a0 = fabs(x0), s0 = sg(a0);
-      if (sg.ok) nbad += !same(s0, sqrt(a0));
-      SqrtGroup sh;  // negative, NaN, tiny, huge arguments must be flagged, never answered wrongly
-      const double s1 = sh(x1);
-      if (sh.ok) nbad += !same(s1, sqrt(x1));
+    {  // square roots: plain, zero-aware, and of arguments that must be flagged (negative, NaN, tiny, huge)
+      FastMath fa, fb, fc;
+      const double a0 = fabs(x0), s0 = fa.sqrt(a0), s1 = fb.sqrt_z((it & 3) ? fabs(x1) : 0.0), s2 = fc.sqrt(x2);
+      if (fa.ok) nbad += !same(s0, sqrt(a0));
+      if (fb.ok) nbad += !same(s1, sqrt((it & 3) ? fabs(x1) : 0.0));
+      if (fc.ok) nbad += !same(s2, sqrt(x2));
     }
-    DivGroup d3(3.0, kRcpConst[0]), d9(9.0, kRcpConst[1]), d54(54.0, kRcpConst[2]);
-    const double c0 = d3(x0), c1 = d9(x1), c2 = d54(x2);
-    if (d3.ok) nbad += !same(c0, x0 / 3);
-    if (d9.ok) nbad += !same(c1, x1 / 9);
-    if (d54.ok) nbad += !same(c2, x2 / 54);
+    {  // the constant divisors of solveP3
+      FastMath f3, f9, f54;
+      const double c0 = f3.div(x0, f3.divisor(3.0, kRcpConst[0])), c1 = f9.div_z(x1, f9.divisor(9.0, kRcpConst[1]));
+      const double c2 = f54.div(x2, f54.divisor(54.0, kRcpConst[2]));
+      if (f3.ok) nbad += !same(c0, x0 / 3);
+      if (f9.ok) nbad += !same(c1, x1 / 9);
+      if (f54.ok) nbad += !same(c2, x2 / 54);
+    }
   }
   atomicAdd(bad, nbad);
   atomicAdd(slow, nslow);
@@ -80,7 +84,7 @@ int main(int argc, char** argv) {
   for (int r = 0; r < rounds; r++) k<<<blocks, threads>>>(0x1234567ull + (unsigned long long)r * blocks * threads * 64, d, d + 1);
   cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   const double groups = (double)rounds * blocks * threads * 64;
-  printf("divcheck: %.3e divisor groups (3 shared-divisor + 3 constant-divisor quotients + 2 square roots each), %llu differing results, "
+  printf("divcheck: %.3e divisor groups (3 shared-divisor + 3 constant-divisor quotients + 3 square roots each), %llu differing results, "
          "%.2f%% of the groups left the fast range  (%s)\n",
          groups, h[0], 100.0 * h[1] / groups, cudaGetErrorString(cudaGetLastError()));
   return h[0] != 0;
