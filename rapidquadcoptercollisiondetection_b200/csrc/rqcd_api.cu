@@ -57,6 +57,7 @@ struct rqcd_ctx {
   // staging for host-pointer calls
   DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group;
   int refill_min = 0;  // RQCD_REFILL_MIN override; 0 = chosen from the obstacle count
+  int lockstep = -1;   // RQCD_LOCKSTEP override (0/1); -1 = chosen from the obstacle count
   unsigned long long launches = 0;
   char last_error[512] = {0};
 };
@@ -183,6 +184,8 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   // idle lane costs a slot in every frame until then; trajectories over many obstacles finish rarely, so they fetch
   // eagerly (measured optima on B200: 2 at M = 256, 4 at M = 64, 8 at M = 5)
   p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (p.m >= 128 ? 2 : (p.m >= 16 ? 4 : 8));
+  // measured on B200: free-running warps win from ~128 obstacles per trajectory on (C5 +7 %), lockstep below
+  p.lockstep = ctx->lockstep >= 0 ? ctx->lockstep : (p.m >= 128 ? 0 : 1);
   p.work_counter = ctx->d_counter;
   const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->stride, moving);
   if (smem > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
@@ -406,6 +409,8 @@ int rqcd_create(rqcd_ctx** out, int device) {
   if (hc && atoll(hc) > 0) ctx->chunk_override = atoll(hc);
   const char* rm = getenv("RQCD_REFILL_MIN");
   if (rm && atoi(rm) >= 1 && atoi(rm) <= 32) ctx->refill_min = atoi(rm);
+  const char* ls = getenv("RQCD_LOCKSTEP");
+  if (ls && (ls[0] == '0' || ls[0] == '1') && ls[1] == 0) ctx->lockstep = ls[0] - '0';
   *out = ctx;
   return RQCD_OK;
 }

@@ -30,9 +30,6 @@ namespace rqcd {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-#ifndef RQCD_LOCKSTEP
-#define RQCD_LOCKSTEP 1
-#endif
 
 
 // ---- TMA bulk copy global -> shared (1-D), completion on an mbarrier ---------------------------------
@@ -164,20 +161,20 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
   int n_have = 0;
   unsigned long long avail = 0;  // candidates known to have arrived (streaming input)
   for (;;) {
-#if RQCD_LOCKSTEP == 1
-    // ---- CTA barrier once per trip: the warps of a CTA walk the (larger than the 32 KB instruction cache) loop
-    // body in step, so an instruction line fetched from L2 serves all of them; the same instruction counts the
-    // CTA's idle lanes for the work-queue trigger
-    n_have = __syncthreads_count(have);
-    const bool fetch_now = (kThreads - n_have >= p.refill_min * (kThreads / 32)) || n_have == 0;
-#else
-    const bool fetch_now = true;
-#endif
+    // ---- CTA lockstep (p.lockstep, chosen per launch): one barrier per trip keeps the warps of a CTA in the same
+    // part of the loop body, which is larger than the instruction cache, so an instruction line fetched from L2
+    // serves all of them; the same instruction counts the CTA's idle lanes for the work-queue trigger. Long obstacle
+    // tables (few fetches, long uninterrupted runs of frames) do better with free-running warps.
+    bool fetch_now = true;
+    if (p.lockstep) {
+      n_have = __syncthreads_count(have);
+      fetch_now = (kThreads - n_have >= p.refill_min * (kThreads / 32)) || n_have == 0;
+    }
     // ---- work queue: idle lanes take new candidates
     const unsigned need = __ballot_sync(kFull, !have);
     if (need != 0 && !exhausted && fetch_now) {
       const int cnt = __popc(need);
-      if (RQCD_LOCKSTEP || cnt >= p.refill_min || need == kFull) {
+      if (p.lockstep || cnt >= p.refill_min || need == kFull) {
         unsigned long long b = 0;
         if (lane == 0) b = atomicAdd(p.work_counter, (unsigned long long)cnt);
         b = __shfl_sync(kFull, b, 0);
@@ -270,14 +267,14 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
         }
       }
     }
-#if RQCD_LOCKSTEP == 1
-    // nothing anywhere in the CTA, the fetch above brought nothing and every warp has seen the queue run dry (a
-    // fetch can also come back empty-handed when the planner's earlier stages rejected all it took)
-    if (n_have == 0 && __syncthreads_count(have || !exhausted) == 0) break;
-    if (__ballot_sync(kFull, have) == 0) continue;  // this warp is done; keep meeting the CTA at the barrier
-#else
-    if (exhausted && __ballot_sync(kFull, have) == 0) break;
-#endif
+    if (p.lockstep) {
+      // nothing anywhere in the CTA, the fetch above brought nothing and every warp has seen the queue run dry (a
+      // fetch can also come back empty-handed when the planner's earlier stages rejected all it took)
+      if (n_have == 0 && __syncthreads_count(have || !exhausted) == 0) break;
+      if (__ballot_sync(kFull, have) == 0) continue;  // this warp is done; keep meeting the CTA at the barrier
+    } else {
+      if (exhausted && __ballot_sync(kFull, have) == 0) break;
+    }
 
     int pv = -1;  // verdict of the pair that completed in this trip, if any
 

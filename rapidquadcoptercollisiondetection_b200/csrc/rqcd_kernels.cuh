@@ -59,6 +59,7 @@ struct CheckParams {
   // control
   int early_exit;
   int refill_min;          // idle lanes per warp that trigger a work-queue fetch
+  int lockstep;            // 1: the warps of a CTA meet at a barrier every trip (see k_check)
   unsigned long long* work_counter;
   BlockPartial* partials;  // [gridDim.x]
   // streaming input (host-pointer calls): candidates [0, *progress) have arrived in `in`; null = all present.
