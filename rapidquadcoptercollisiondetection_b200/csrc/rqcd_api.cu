@@ -180,10 +180,10 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   p.m = cc.pairwise ? 1 : ctx->m;
   p.mp = ctx->mp;
   p.stride = ctx->stride;
-  // idle lanes per warp (CTA average) that trigger a work-queue fetch: a fetch costs a divergent generate pass, an
-  // idle lane costs a slot in every frame until then; trajectories over many obstacles finish rarely, so they fetch
-  // eagerly (measured optima on B200: 2 at M = 256, 4 at M = 64, 8 at M = 5)
-  p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (p.m >= 128 ? 2 : (p.m >= 16 ? 4 : 8));
+  // idle lanes per warp (CTA average) that trigger a work-queue fetch: a fetch costs a pass in which only the
+  // fetching lanes (and, for a few of them, the helpers that build their axes) work, an idle lane costs a slot in
+  // every frame until then (measured optima on B200: 4 at M = 5, 64 and 256; 8 for the pairwise shape)
+  p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (cc.pairwise ? 8 : 4);
   // measured on B200: free-running warps win from ~128 obstacles per trajectory on (C5 +7 %), lockstep below
   p.lockstep = ctx->lockstep >= 0 ? ctx->lockstep : (p.m >= 128 ? 0 : 1);
   p.work_counter = ctx->d_counter;

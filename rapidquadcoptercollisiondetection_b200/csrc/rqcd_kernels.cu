@@ -30,6 +30,7 @@ namespace rqcd {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kCoopOwners = 10;  // new candidates a warp builds cooperatively in one pass (3 lanes each)
 
 
 // ---- TMA bulk copy global -> shared (1-D), completion on an mbarrier ---------------------------------
@@ -199,20 +200,81 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
           }
         }
         bool fresh = false;
-        if (!have) {
-          const long long i = (long long)b + __popc(need & lt_mask);
-          const bool rejected = (i < p.n) && arrived && p.skip && p.skip[i] != 0;  // planner: dropped by an earlier stage
-          if (i < p.n && arrived && !rejected) {
-            idx = i;
-            double t0, t1, cost;
-            load_trajectory<MODE>(p, i, c, t0, t1, cost);
-            if (MODE == MODE_BC) {
-              if (p.cost) p.cost[i] = cost;
-              if (p.coeffs) {
+        const long long my_i = (long long)b + __popc(need & lt_mask);
+        // planner: skip[i] != 0 was dropped by an earlier stage
+        const bool take = !have && my_i < p.n && arrived && !(p.skip && p.skip[my_i] != 0);
+        double t0 = 0.0, t1 = 0.0, cost = 0.0;
+        V3 x0 = v3(0, 0, 0), x1 = v3(0, 0, 0);
+        double amax = 0.0;
+        const unsigned owners = __ballot_sync(kFull, take);
+        const int n_own = __popc(owners);
+        if (MODE == MODE_BC && n_own <= kCoopOwners) {
+          // RapidTrajectoryGenerator::Generate + GetTrajectory for a FEW new candidates by the whole warp: the three
+          // axes of a primitive are independent (SingleAxisTrajectory), so lane 3q + a builds axis a of the q-th new
+          // candidate and the owner collects its 18 coefficients with shuffles. Same arithmetic per axis as
+          // load_trajectory; a handful of idle lanes no longer walk three axes one after the other while 28 wait.
+          const int my_rank = __popc(owners & lt_mask);
+          const int q = lane / 3, ax = lane % 3;
+          double tc[6] = {0, 0, 0, 0, 0, 0}, t_cost = 0.0, t_x0 = 0.0, t_x1 = 0.0, t_am = 0.0, t_tf = 0.0;
+          if (lane < 3 * kCoopOwners && q < n_own) {
+            const unsigned own = __fns(owners, 0, q + 1);
+            const long long i = (long long)b + __popc(need & ((1u << own) - 1u));
+            const double* d = p.in;
+            const long long st = p.in_stride;
+            const double Tf = ld_in(d + 18 * st + i);
+            const double p0 = ld_in(d + (0 + ax) * st + i), v0 = ld_in(d + (3 + ax) * st + i), a0 = ld_in(d + (6 + ax) * st + i);
+            const double pf = ld_in(d + (9 + ax) * st + i), vf = ld_in(d + (12 + ax) * st + i), af = ld_in(d + (15 + ax) * st + i);
+            const AxisParams g = gen_axis(p0, v0, a0, pf, vf, af, (p.goal_mask >> (3 * ax)) & 1,
+                                          (p.goal_mask >> (3 * ax + 1)) & 1, (p.goal_mask >> (3 * ax + 2)) & 1, Tf);
+            axis_coeffs(g, p0, v0, a0, tc[0], tc[1], tc[2], tc[3], tc[4], tc[5]);
+            t_cost = g.cost;
+            t_tf = Tf;
+            if (p.coeffs) {
 #pragma unroll
-                for (int j = 0; j < 18; j++) p.coeffs[j * p.coeff_stride + i] = c[j];
-              }
+              for (int j = 0; j < 6; j++) p.coeffs[(3 * j + ax) * p.coeff_stride + i] = tc[j];
             }
+            // this axis' share of X(t_start = 0), X(t_end = Tf) and of the side filter's bound
+            t_x0 = poly5(tc[0], tc[1], tc[2], tc[3], tc[4], tc[5], 0.0);
+            t_x1 = poly5(tc[0], tc[1], tc[2], tc[3], tc[4], tc[5], Tf);
+            const double T = fabs(Tf);
+#pragma unroll
+            for (int j = 0; j < 6; j++) t_am = t_am * T + fabs(tc[j]);
+          }
+          __syncwarp();
+          const int src = take ? 3 * my_rank : 0;
+#pragma unroll
+          for (int j = 0; j < 6; j++) {
+            const double ca = __shfl_sync(kFull, tc[j], src), cb = __shfl_sync(kFull, tc[j], src + 1);
+            const double cc = __shfl_sync(kFull, tc[j], src + 2);
+            if (take) c[3 * j] = ca, c[3 * j + 1] = cb, c[3 * j + 2] = cc;
+          }
+          const double k0 = __shfl_sync(kFull, t_cost, src), k1 = __shfl_sync(kFull, t_cost, src + 1);
+          const double k2 = __shfl_sync(kFull, t_cost, src + 2);
+          x0 = v3(__shfl_sync(kFull, t_x0, src), __shfl_sync(kFull, t_x0, src + 1), __shfl_sync(kFull, t_x0, src + 2));
+          x1 = v3(__shfl_sync(kFull, t_x1, src), __shfl_sync(kFull, t_x1, src + 1), __shfl_sync(kFull, t_x1, src + 2));
+          amax = __shfl_sync(kFull, t_am, src) + __shfl_sync(kFull, t_am, src + 1) + __shfl_sync(kFull, t_am, src + 2);
+          t1 = __shfl_sync(kFull, t_tf, src);
+          cost = k0 + k1 + k2;  // GetCost: cost[0] + cost[1] + cost[2] (.hpp:214-216)
+          if (take && p.cost) p.cost[my_i] = cost;
+        } else if (take) {
+          load_trajectory<MODE>(p, my_i, c, t0, t1, cost);
+          if (MODE == MODE_BC) {
+            if (p.cost) p.cost[my_i] = cost;
+            if (p.coeffs) {
+#pragma unroll
+              for (int j = 0; j < 18; j++) p.coeffs[j * p.coeff_stride + my_i] = c[j];
+            }
+          }
+          if (!MOVING) {
+            x0 = traj_value(c, t0);
+            x1 = traj_value(c, t1);
+            amax = side_filter_bound(c, t0, t1);
+          }
+        }
+        if (take) {
+          {
+            const long long i = my_i;
+            idx = i;
             RQCD_SLOT(SLOT_T0) = t0;
             RQCD_SLOT(SLOT_T1) = t1;
             RQCD_SLOT(SLOT_COST) = cost;
@@ -221,9 +283,9 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
               for (int j = 0; j < 18; j++) base[j * kThreads + tid] = c[j];
             } else {
               // X(t_start), X(t_end) of the trajectory and the side filter's bound: the same for every obstacle
-              ends.set_xs(traj_value(c, t0));
-              ends.set_xf(traj_value(c, t1));
-              ends.set_amax(side_filter_bound(c, t0, t1));
+              ends.set_xs(x0);
+              ends.set_xf(x1);
+              ends.set_amax(amax);
             }
             if (PAIRWISE) {
               sph.cx = ld_in(p.spheres + i);
