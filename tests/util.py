@@ -102,3 +102,34 @@ def degenerate_case():
         {"type": "prism", "center": [0.0, 0.0, 0.0], "side": [0.3, 0.2, 0.1], "quat": [0.0, 0.0, 0.0, 0.0]},  # zero quaternion
     ]
     return bc, specs
+
+
+def grazing_case(n=20_000, seed=2024, log_a=(1.0, 8.0)):
+    """Trajectories that come within rounding noise of an obstacle's surface at a critical time:
+    x(t) = A (t - t*)^2 + E (t - t*)^5 + 1 + delta, y(t) = b (t - t*), z = 0 against the unit sphere at the origin and
+    the face x = 1 of two prisms (+ 17 far spheres). A quintic term is needed: the reference's solver divides by zero
+    on velocity polynomials of degree < 3. A = 10^U(log_a): from ~1e3 on the reference's closed-form roots are off by
+    more than delta / A (cancellation in q cos(.) - a/3), and WHICH side of the plane the computed critical point
+    lands on is decided by the last bits of libm's acos / cos / pow."""
+    rng = np.random.default_rng(seed)
+    t_end = rng.uniform(0.5, 1.5, n)
+    ts = rng.uniform(0.1, 0.9, n) * t_end
+    A = 10.0 ** rng.uniform(log_a[0], log_a[1], n)
+    E = rng.choice([-1.0, 1.0], n) * rng.uniform(0.5, 2.0, n)
+    delta = rng.choice([-1.0, 1.0], n) * 10.0 ** rng.uniform(-13, -6, n)
+    bq = rng.uniform(-1e-2, 1e-2, n)
+    coeffs = np.zeros((18, n))
+    coeffs[0] = E
+    coeffs[3] = -5 * E * ts
+    coeffs[6] = 10 * E * ts**2
+    coeffs[9] = -10 * E * ts**3 + A
+    coeffs[12] = 5 * E * ts**4 - 2 * A * ts
+    coeffs[15] = -E * ts**5 + A * ts * ts + 1.0 + delta
+    coeffs[13] = bq
+    coeffs[16] = -bq * ts
+    specs = [
+        {"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 1.0},
+        {"type": "prism", "center": [0.0, 0.0, 0.0], "side": [2.0, 2.0, 2.0], "quat": [1.0, 0, 0, 0]},
+        {"type": "prism", "center": [0.0, 0.0, 0.0], "side": [2.0, 1.0, 3.0], "quat": [0.9238795325112867, 0.3826834323650898, 0, 0]},
+    ] + [{"type": "sphere", "center": [3.0 + k, 1.0, 0.0], "radius": 0.5} for k in range(17)]
+    return coeffs, t_end, specs
