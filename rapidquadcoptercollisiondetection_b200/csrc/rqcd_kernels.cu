@@ -110,14 +110,13 @@ RQCD_DEV void load_trajectory(const CheckParams& p, long long i, double (&c)[18]
 template <int MODE, bool MOVING, bool PAIRWISE, bool ENDBITS>
 __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const CheckParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int kWarps = kThreads / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = PAIRWISE ? 1 : p.m, mp = p.mp;
 
   double* tab = reinterpret_cast<double*>(smem_raw);
   int* oflags = reinterpret_cast<int*>(tab + (size_t)p.stride * mp);
-  unsigned long long* wcnt = reinterpret_cast<unsigned long long*>(oflags + mp);  // [kWarps][8]
-  double* bcost = reinterpret_cast<double*>(wcnt + kWarps * 8);                   // [kThreads]
+  unsigned long long* tcnt = reinterpret_cast<unsigned long long*>(oflags + mp);  // [8][kThreads]: verdict counters
+  double* bcost = reinterpret_cast<double*>(tcnt + 8 * kThreads);                 // [kThreads]
   long long* bidx = reinterpret_cast<long long*>(bcost + kThreads);               // [kThreads]
   double* slot = reinterpret_cast<double*>(bidx + kThreads);                      // [kSlotRows][kThreads]: EndPoints rows
   double* base = slot + kSlotRows * kThreads;                                     // MOVING: [18][kThreads]
@@ -130,7 +129,8 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
 
   const uint32_t blob_bytes = (uint32_t)(((size_t)p.stride * mp) * 8 + (size_t)mp * 4);
   if (tid == 0) mbar_init(&mbar, 1);
-  if (tid < kWarps * 8) wcnt[tid] = 0ull;
+#pragma unroll
+  for (int j = 0; j < 8; j++) tcnt[j * kThreads + tid] = 0ull;
   bcost[tid] = __longlong_as_double(0x7ff0000000000000ll);
   bidx[tid] = -1;
   __syncthreads();
@@ -437,27 +437,16 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
       k++;
     }
     const bool fin = have && !in_pair && (k >= m || (p.early_exit && verdict != 0));
-    if (__any_sync(kFull, fin)) {
-      // warp-level sums of the finishing lanes' counters (REDUX), one shared-memory update by lane 0
-      const unsigned n1 = fin ? (pair_hits & 0xffffu) : 0u, n2 = fin ? (pair_hits >> 16) : 0u;  // k <= m < 2^16
-      const unsigned n3 = fin ? depth_cap_hits : 0u, nk = fin ? (unsigned)k : 0u;
-      const unsigned s1 = __reduce_add_sync(kFull, n1), s2 = __reduce_add_sync(kFull, n2);
-      const unsigned s3 = __reduce_add_sync(kFull, n3), sk = __reduce_add_sync(kFull, nk);
-      const int tv = fin ? verdict : -1;
-      const unsigned q0 = __ballot_sync(kFull, tv == 0), q1 = __ballot_sync(kFull, tv == 1);
-      const unsigned q2 = __ballot_sync(kFull, tv == 2), q3 = __ballot_sync(kFull, tv == 3);
-      if (lane == 0) {
-        unsigned long long* w = wcnt + warp * 8;
-        w[0] += __popc(q0);
-        w[1] += __popc(q1);
-        w[2] += __popc(q2);
-        w[3] += __popc(q3);
-        w[4] += sk - s1 - s2 - s3;
-        w[5] += s1;
-        w[6] += s2;
-        w[7] += s3;
-      }
+    {
       if (fin) {
+        // the finishing lane adds its trajectory to its own counter rows (summed over the CTA at the end)
+        const unsigned n1 = pair_hits & 0xffffu, n2 = pair_hits >> 16;  // k <= m < 2^16
+        unsigned long long* t = tcnt + tid;
+        t[verdict * kThreads] += 1ull;
+        t[4 * kThreads] += (unsigned)k - n1 - n2 - depth_cap_hits;
+        t[5 * kThreads] += n1;
+        t[6 * kThreads] += n2;
+        if (depth_cap_hits) t[7 * kThreads] += depth_cap_hits;
         if (p.verdict) p.verdict[idx] = (uint8_t)verdict;
         if (p.first_obstacle) p.first_obstacle[idx] = first;
         const double cost = RQCD_SLOT(SLOT_COST);
@@ -494,11 +483,15 @@ __global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const Check
       }
     }
     BlockPartial* out = p.partials + blockIdx.x;
-    if (lane < 8) {
+    for (int j = 0; j < 8; j++) {
       unsigned long long s = 0;
-      for (int w = 0; w < kWarps; w++) s += wcnt[w * 8 + lane];
-      if (lane < 4) out->traj[lane] = s;
-      else out->pair[lane - 4] = s;
+      for (int q = lane; q < kThreads; q += 32) s += tcnt[j * kThreads + q];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(kFull, s, off);
+      if (lane == 0) {
+        if (j < 4) out->traj[j] = s;
+        else out->pair[j - 4] = s;
+      }
     }
     if (lane == 0) {
       out->best_cost = bc;
@@ -860,7 +853,7 @@ cudaError_t init_device_constants(cudaStream_t s) {
 
 size_t check_smem_bytes(int mp, int stride, bool moving) {
   size_t b = (size_t)stride * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
-  b += (kThreads / 32) * 8 * 8;                           // warp counters
+  b += (size_t)8 * kThreads * 8;                          // verdict counters, one row of 8 per thread
   b += (size_t)kThreads * 16;                             // best cost / index per thread
   b += (size_t)kThreads * 8 * EndPoints::kRows;           // X(t_start), X(t_end), side-filter bound per thread
   if (moving) b += (size_t)18 * kThreads * 8;             // the lane's own coefficients
