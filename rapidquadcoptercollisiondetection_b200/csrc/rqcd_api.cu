@@ -180,12 +180,14 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   p.m = cc.pairwise ? 1 : ctx->m;
   p.mp = ctx->mp;
   p.stride = ctx->stride;
-  // idle lanes per warp (CTA average) that trigger a work-queue fetch: a fetch costs a pass in which only the
-  // fetching lanes (and, for a few of them, the helpers that build their axes) work, an idle lane costs a slot in
-  // every frame until then (measured optima on B200: 4 at M = 5, 64 and 256; 8 for the pairwise shape)
-  p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (cc.pairwise ? 8 : 4);
-  // measured on B200: free-running warps win from ~128 obstacles per trajectory on (C5 +7 %), lockstep below
-  p.lockstep = ctx->lockstep >= 0 ? ctx->lockstep : (p.m >= 128 ? 0 : 1);
+  // CTA lockstep or free-running warps, and the idle lanes per warp that trigger a work-queue fetch (in lockstep:
+  // the CTA's average): a fetch costs a pass in which only the fetching lanes (and, for a few of them, the helpers
+  // that build their axes) work, an idle lane costs a slot in every frame until then. Measured optima on B200
+  // (final build): tables of 16+ obstacles run free (C3 +7 %, C4 +3 %, C5 +4 % over lockstep) and fetch at 6 idle
+  // lanes (4 from 128 obstacles on); the Forest shape (5 obstacles, early exit) and the pairwise shape, whose
+  // warps fetch every other trip, stay in lockstep (which also aligns their fetches) at 4 and 8.
+  p.lockstep = ctx->lockstep >= 0 ? ctx->lockstep : ((!cc.pairwise && p.m >= 16) ? 0 : 1);
+  p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (cc.pairwise ? 8 : (p.m >= 128 ? 4 : (p.m >= 16 ? 6 : 4)));
   p.work_counter = ctx->d_counter;
   const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->stride, moving);
   if (smem > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
