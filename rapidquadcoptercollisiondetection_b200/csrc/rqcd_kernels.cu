@@ -107,8 +107,13 @@ RQCD_DEV void load_trajectory(const CheckParams& p, long long i, double (&c)[18]
   }
 }
 
+#ifdef RQCD_MAXNREG  // kernel-variant experiments: an explicit register cap instead of a resident-CTA target
+#define RQCD_CHECK_BOUNDS __maxnreg__(RQCD_MAXNREG)
+#else
+#define RQCD_CHECK_BOUNDS __launch_bounds__(kThreads, RQCD_MIN_BLOCKS)
+#endif
 template <int MODE, bool MOVING, bool PAIRWISE, bool ENDBITS>
-__global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check(const CheckParams p) {
+__global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = PAIRWISE ? 1 : p.m, mp = p.mp;
