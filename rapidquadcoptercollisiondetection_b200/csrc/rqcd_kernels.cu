@@ -505,279 +505,6 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
   }
 }
 
-
-// ---------------------------------------------------------------------------------------------------------------
-// k_check_uni: the same check, all pairs against a static table, organised around the FIRST frame of a pair. 80 % of
-// all frames are first frames (C3: 1.245 frames per pair), and a first frame is special: its interval is the whole
-// window, so its midpoint and X(mid) are the same for every obstacle of a trajectory, and if all 32 lanes of a warp
-// take their first frames against the SAME obstacle the shape test is a warp-uniform branch (a sphere skips the
-// prism's rotations) and no lane runs on stale data.
-//   * a warp takes 32 candidates at a time and builds them with all 32 lanes;
-//   * phase A trip: obstacle k for every lane -- frame_at() with the stored X(mid); a pair that needs children
-//     pushes its one or two child intervals, tagged k, on the lane's stack (low child below high child: the
-//     reference's depth-first order);
-//   * phase B trip, taken when at least `phase_b_min` lanes have parked intervals (or the table is through): every
-//     such lane pops one interval and runs the general frame on it; children go back on the stack, a result other
-//     than NoCollision decides the pair and drops its remaining intervals (they sit on top of the stack);
-//   * when the table is through and the stacks are empty the 32 trajectories are finished together.
-// Pair verdicts arrive out of obstacle order, so the trajectory's verdict is kept as the one of the LOWEST obstacle
-// index (ForestPerformanceEval.cpp:216-225 breaks at the first in index order).
-constexpr int kUniStack = 64;       // parked intervals per lane: kUniStackHigh + 2 from a first frame + kMaxDepth
-constexpr int kUniStackHigh = 22;   // a lane this deep forces phase B
-constexpr int kUniRows = EndPoints::kRows + 3;  // + X(mid of the whole window)
-
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check_uni(const CheckParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int m = p.m, mp = p.mp;
-  double* tab = reinterpret_cast<double*>(smem_raw);
-  int* oflags = reinterpret_cast<int*>(tab + (size_t)p.stride * mp);
-  unsigned long long* tcnt = reinterpret_cast<unsigned long long*>(oflags + mp);  // [8][kThreads]
-  double* bcost = reinterpret_cast<double*>(tcnt + 8 * kThreads);
-  long long* bidx = reinterpret_cast<long long*>(bcost + kThreads);
-  double* slot = reinterpret_cast<double*>(bidx + kThreads);                      // [kUniRows][kThreads]
-  unsigned* inbits = reinterpret_cast<unsigned*>(slot + kUniRows * kThreads);     // [(mp + 31) / 32][kThreads]
-  __shared__ __align__(8) uint64_t mbar;
-
-  const uint32_t blob_bytes = (uint32_t)(((size_t)p.stride * mp) * 8 + (size_t)mp * 4);
-  if (tid == 0) mbar_init(&mbar, 1);
-#pragma unroll
-  for (int j = 0; j < 8; j++) tcnt[j * kThreads + tid] = 0ull;
-  bcost[tid] = __longlong_as_double(0x7ff0000000000000ll);
-  bidx[tid] = -1;
-  __syncthreads();
-  if (blob_bytes > 0) {
-    if (tid == 0) tma_bulk_g2s(tab, p.obs_blob, blob_bytes, &mbar);
-    mbar_wait(&mbar, 0);
-  }
-
-  double c[18];
-#pragma unroll
-  for (int j = 0; j < 18; j++) c[j] = 0.0;
-  EndPoints ends;
-  ends.slot = slot + tid;
-  ends.stride = kThreads;
-  double* xm_row = slot + EndPoints::kRows * kThreads + tid;
-  double2 stack[kUniStack];
-  int stack_k[kUniStack];
-  unsigned long long avail = 0;
-  bool exhausted = false;
-
-  while (!exhausted) {
-    // ---- a batch of 32 candidates
-    unsigned long long b = 0;
-    if (lane == 0) b = atomicAdd(p.work_counter, 32ull);
-    b = __shfl_sync(kFull, b, 0);
-    if (b >= (unsigned long long)p.n) break;
-    if (b + 32ull >= (unsigned long long)p.n) exhausted = true;
-    if (p.progress) {  // streaming input: wait until the copy engine has delivered the whole batch
-      unsigned long long want = b + 32ull;
-      if (want > (unsigned long long)p.n) want = (unsigned long long)p.n;
-      bool arrived = true;
-      if (want > avail) {
-        const long long t_begin = clock64();
-        for (;;) {
-          avail = *reinterpret_cast<const volatile unsigned long long*>(p.progress);
-          if (avail >= want) break;
-          if (clock64() - t_begin > (1ll << 32)) {  // ~2 s: the copy never came; fail the call instead of hanging
-            if (lane == 0) atomicExch(p.stream_error, 1ull);
-            arrived = false;
-            break;
-          }
-          __nanosleep(256);
-        }
-      }
-      if (!arrived) break;
-    }
-    const long long idx = (long long)b + lane;
-    const bool have = idx < p.n && !(p.skip && p.skip[idx] != 0);  // planner: dropped by an earlier stage
-    double t0 = 0.0, t1 = 0.0, cost = 0.0;
-    if (have) {
-      load_trajectory<MODE>(p, idx, c, t0, t1, cost);
-      if (MODE == MODE_BC) {
-        if (p.cost) p.cost[idx] = cost;
-        if (p.coeffs) {
-#pragma unroll
-          for (int j = 0; j < 18; j++) p.coeffs[j * p.coeff_stride + idx] = c[j];
-        }
-      }
-      ends.set_xs(traj_value(c, t0));
-      ends.set_xf(traj_value(c, t1));
-      ends.set_amax(side_filter_bound(c, t0, t1));
-      const V3 xm = traj_value(c, (t0 + t1) / 2);  // the first frame's midpoint (CollisionChecker.cpp:87), every obstacle
-      xm_row[0] = xm.x, xm_row[kThreads] = xm.y, xm_row[2 * kThreads] = xm.z;
-    }
-    {
-      // CollisionCheck's end-point tests (CollisionChecker.cpp:73-77) against the whole table, by the whole warp: lane j
-      // tests obstacles j, j + 32, ... against the end points of one trajectory at a time
-      unsigned todo = __ballot_sync(kFull, have);
-      __syncwarp();
-      while (todo) {
-        const int owner = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const double* row = slot + (tid - lane + owner);
-        const V3 Xs = v3(row[0], row[kThreads], row[2 * kThreads]);
-        const V3 Xf = v3(row[3 * kThreads], row[4 * kThreads], row[5 * kThreads]);
-        for (int k0 = 0; k0 < m; k0 += 32) {
-          const int kk = k0 + lane;
-          bool inside = false;
-          if (kk < m) {
-            TableObs o;
-            o.rec = tab + (size_t)kk * p.stride;
-            o.flags = oflags[kk];
-            inside = ends_inside(o, Xs, Xf);
-          }
-          const unsigned bits = __ballot_sync(kFull, inside);
-          if (lane == owner) inbits[(k0 >> 5) * kThreads + tid] = bits;
-        }
-      }
-      __syncwarp();
-    }
-
-    int sp = 0, verdict = 0, first = -1;
-    unsigned n1 = 0, n2 = 0, n3 = 0;  // this trajectory's Collision / Indeterminable / depth-cap pairs
-    // a pair decided other than NoCollision: counters, matrix entry, the trajectory's verdict = lowest obstacle index
-#define RQCD_DECIDE(kk, v)                                                          \
-  {                                                                                 \
-    if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + (kk)] = (uint8_t)(v); \
-    n1 += ((v) == 1), n2 += ((v) == 2), n3 += ((v) == 3);                           \
-    if (first < 0 || (kk) < first) first = (kk), verdict = (v);                     \
-  }
-    // drop the pair's parked intervals: they are the top of the stack
-#define RQCD_DROP(kk) \
-  while (sp > 0 && stack_k[sp - 1] == (kk)) --sp;
-
-    int k = 0;
-    for (;;) {
-      const unsigned pend = __ballot_sync(kFull, sp > 0);
-      const bool deep = __any_sync(kFull, sp >= kUniStackHigh);
-      if (k < m && !deep && __popc(pend) < p.phase_b_min) {
-        // ---- phase A: the first frame of (trajectory, obstacle k) on every lane
-        const bool bit = (inbits[(k >> 5) * kThreads + tid] >> (k & 31)) & 1u;
-        const bool active = have & !bit;
-        UniformObs o;
-        o.rec = tab + (size_t)k * p.stride;
-        o.flags = oflags[k];
-        Children ch;
-        const V3 xm = v3(xm_row[0], xm_row[kThreads], xm_row[2 * kThreads]);
-        const int r = frame_at<false>(c, t0, t1, (t0 + t1) / 2, xm, ends, false, active, o, p.min_t, ch);
-        if (have) {
-          if (bit) {
-            RQCD_DECIDE(k, 1)  // an end point of the trajectory is inside: Collision without a section (:73-77)
-          } else if (r == STEP_CHILD) {
-            if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)0;  // until a child says otherwise
-            // low child [t0, .] below high child [., t1]
-            if (ch.has_hi & ch.has_lo) {
-              stack[sp] = make_double2(t0, ch.lo_tf), stack_k[sp] = k, sp++;
-              stack[sp] = make_double2(ch.t_next, t1), stack_k[sp] = k, sp++;
-            } else if (ch.has_hi) {
-              stack[sp] = make_double2(ch.t_next, t1), stack_k[sp] = k, sp++;
-            } else {
-              stack[sp] = make_double2(t0, ch.t_next), stack_k[sp] = k, sp++;
-            }
-          } else if (r != STEP_CLEAR) {
-            RQCD_DECIDE(k, r)
-          } else if (p.verdict_matrix) {
-            p.verdict_matrix[idx * (long long)m + k] = (uint8_t)0;
-          }
-        }
-        k++;
-      } else if (pend != 0) {
-        // ---- phase B: one parked interval per lane that has any
-        const bool work = sp > 0;
-        double ts = t0, tf = t1;
-        int kk = 0;
-        if (work) {
-          --sp;
-          ts = stack[sp].x, tf = stack[sp].y, kk = stack_k[sp];
-        }
-        TableObs o;
-        o.rec = tab + (size_t)kk * p.stride;
-        o.flags = oflags[kk];
-        Children ch;
-        const int r = frame<false>(c, ts, tf, ends, false, work, o, p.min_t, ch);
-        if (work) {
-          if (r == STEP_CHILD) {
-            const int need = (ch.has_hi & ch.has_lo) ? 2 : 1;
-            if (sp + need > kUniStack) {  // deeper than RQCD_MAX_DEPTH: verdict 3, never silent truncation
-              RQCD_DECIDE(kk, 3)
-              RQCD_DROP(kk)
-            } else if (need == 2) {
-              stack[sp] = make_double2(ts, ch.lo_tf), stack_k[sp] = kk, sp++;
-              stack[sp] = make_double2(ch.t_next, tf), stack_k[sp] = kk, sp++;
-            } else if (ch.has_hi) {
-              stack[sp] = make_double2(ch.t_next, tf), stack_k[sp] = kk, sp++;
-            } else {
-              stack[sp] = make_double2(ts, ch.t_next), stack_k[sp] = kk, sp++;
-            }
-          } else if (r != STEP_CLEAR) {
-            RQCD_DECIDE(kk, r)
-            RQCD_DROP(kk)
-          }
-        }
-      } else {
-        break;
-      }
-    }
-#undef RQCD_DECIDE
-#undef RQCD_DROP
-
-    // ---- the batch is through
-    if (have) {
-      unsigned long long* t = tcnt + tid;
-      t[verdict * kThreads] += 1ull;
-      t[4 * kThreads] += (unsigned)m - n1 - n2 - n3;
-      t[5 * kThreads] += n1;
-      t[6 * kThreads] += n2;
-      if (n3) t[7 * kThreads] += n3;
-      if (p.verdict) p.verdict[idx] = (uint8_t)verdict;
-      if (p.first_obstacle) p.first_obstacle[idx] = first;
-      if (verdict == 0 && cost < bcost[tid]) {  // indices handed to one lane ascend, so ties keep the lowest
-        bcost[tid] = cost;
-        bidx[tid] = p.index_base + idx;
-      }
-    }
-  }
-
-  // ---- CTA partial
-  __syncthreads();
-  if (tid < 32) {
-    double bc = __longlong_as_double(0x7ff0000000000000ll);
-    long long bi = -1;
-    for (int j = lane; j < kThreads; j += 32) {
-      if (better(bcost[j], bidx[j], bc, bi)) {
-        bc = bcost[j];
-        bi = bidx[j];
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double oc = __shfl_down_sync(kFull, bc, off);
-      const long long oi = __shfl_down_sync(kFull, bi, off);
-      if (better(oc, oi, bc, bi)) {
-        bc = oc;
-        bi = oi;
-      }
-    }
-    BlockPartial* out = p.partials + blockIdx.x;
-    for (int j = 0; j < 8; j++) {
-      unsigned long long s = 0;
-      for (int q = lane; q < kThreads; q += 32) s += tcnt[j * kThreads + q];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(kFull, s, off);
-      if (lane == 0) {
-        if (j < 4) out->traj[j] = s;
-        else out->pair[j - 4] = s;
-      }
-    }
-    if (lane == 0) {
-      out->best_cost = bc;
-      out->best_index = bi;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int nparts, DevSummary* out) {
   __shared__ unsigned long long cnt[8];
   __shared__ double scost[256];
@@ -1100,9 +827,7 @@ const void* check_fn() {
 // cheaper inside the pairs' first frames.
 bool use_endbits(bool moving, bool pairwise, int m) { return !moving && !pairwise && m >= kEndBitsMinObstacles; }
 
-const void* select_check(int mode, bool moving, bool pairwise, int m, bool uni = false) {
-  if (uni) return mode == MODE_BC ? reinterpret_cast<const void*>(&k_check_uni<MODE_BC>)
-                                  : reinterpret_cast<const void*>(&k_check_uni<MODE_COEFF>);
+const void* select_check(int mode, bool moving, bool pairwise, int m) {
   if (pairwise) return check_fn<MODE_BC, false, true, false>();
   if (moving) return mode == MODE_BC ? check_fn<MODE_BC, true, false, false>() : check_fn<MODE_COEFF, true, false, false>();
   if (use_endbits(moving, pairwise, m))
@@ -1119,10 +844,6 @@ int grid_for(long long n, int cap) {
 
 }  // namespace
 
-bool use_uniform(bool moving, bool pairwise, int m, bool early_exit, bool uni) {
-  return uni && use_endbits(moving, pairwise, m) && !early_exit;
-}
-
 cudaError_t init_device_constants(cudaStream_t s) {
   k_init_constants<<<1, 1, 0, s>>>();
   cudaError_t e = cudaGetLastError();
@@ -1135,14 +856,7 @@ cudaError_t init_device_constants(cudaStream_t s) {
   return cudaStreamSynchronize(s);
 }
 
-size_t check_smem_bytes(int mp, int stride, bool moving, bool uni) {
-  if (uni) {
-    size_t u = (size_t)stride * mp * 8 + (size_t)mp * 4;
-    u += (size_t)8 * kThreads * 8 + (size_t)kThreads * 16;
-    u += (size_t)kThreads * 8 * kUniRows;
-    u += (size_t)((mp + 31) / 32) * kThreads * 4;
-    return u;
-  }
+size_t check_smem_bytes(int mp, int stride, bool moving) {
   size_t b = (size_t)stride * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
   b += (size_t)8 * kThreads * 8;                          // verdict counters, one row of 8 per thread
   b += (size_t)kThreads * 16;                             // best cost / index per thread
@@ -1152,14 +866,14 @@ size_t check_smem_bytes(int mp, int stride, bool moving, bool uni) {
   return b;
 }
 
-cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem, bool uni) {
-  return cudaFuncSetAttribute(select_check(mode, moving, pairwise, m, uni), cudaFuncAttributeMaxDynamicSharedMemorySize,
+cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem) {
+  return cudaFuncSetAttribute(select_check(mode, moving, pairwise, m), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)smem);
 }
 
-int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem, bool uni) {
+int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, select_check(mode, moving, pairwise, m, uni), kThreads, smem) !=
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, select_check(mode, moving, pairwise, m), kThreads, smem) !=
       cudaSuccess)
     return 0;
   return nb;
@@ -1167,8 +881,7 @@ int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t 
 
 cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
                          DevSummary* d_summary) {
-  const bool uni = use_uniform(moving, pairwise, p.m, p.early_exit != 0, p.uniform != 0);
-  const size_t smem = check_smem_bytes(pairwise ? 0 : p.mp, pairwise ? 0 : p.stride, moving, uni);
+  const size_t smem = check_smem_bytes(pairwise ? 0 : p.mp, pairwise ? 0 : p.stride, moving);
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
   CheckParams q = p;
@@ -1177,7 +890,7 @@ cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairw
     q.stride = 0;
   }
   void* args[] = {&q};
-  e = cudaLaunchKernel(select_check(mode, moving, pairwise, p.m, uni), dim3(grid), dim3(kThreads), args, smem, s);
+  e = cudaLaunchKernel(select_check(mode, moving, pairwise, p.m), dim3(grid), dim3(kThreads), args, smem, s);
   if (e != cudaSuccess) return e;
   k_finalize<<<1, 256, 0, s>>>(p.partials, grid, d_summary);
   return cudaGetLastError();
