@@ -12,15 +12,21 @@
 //     needs 15 frames for one obstacle does not hold back its 31 neighbours -- they move on to their next
 //     obstacles. The reference's recursion is a per-lane explicit stack of pending [ts, tf] intervals.
 //   * the frame is one converged instruction stream for the whole warp (see frame() in rqcd_device.cuh): the
-//     only divergent regions are the end-point inside tests (sphere vs prism) and the transcendental core of the
-//     cubic solver. The only position a frame evaluates is X(mid): the plane-side tests at the critical times and
-//     at the interval's ends are the sign of a scalar quintic (5 FMAs each) with a certified error margin and a
-//     literal fallback, so an interval is just [ts, tf].
-//   * CTA lockstep: one __syncthreads_count per trip keeps the warps of a CTA in the same part of the loop body,
-//     which is larger than the instruction cache, and counts the CTA's idle lanes.
-//   * work queue: when enough lanes of the CTA have finished their trajectory the warps take new candidates from a
-//     global counter (ballot + popc, one atomicAdd per warp) and the idle lanes build them. With host buffers the
-//     candidates may still be arriving over PCIe: a warp then waits for the copy engine's progress word.
+//     only divergent region is the transcendental core of the cubic solver. The only position a frame evaluates is
+//     X(mid): the plane-side tests at the critical times and at the interval's ends are the sign of a scalar
+//     quintic (5 FMAs each) with a certified error margin and a literal fallback, so an interval is just [ts, tf].
+//     Divisions and square roots are nvcc's in-line sequences with shared reciprocal refinements and ONE range
+//     vote per frame (FastMath / PlainMath).
+//   * CollisionCheck's end-point tests (IsPointInside of X(t_start), X(t_end)) are answered for the whole table when
+//     a trajectory is loaded -- lane = obstacle, one ballot per 32 obstacles -- for tables of 16+ obstacles; shorter
+//     tables, moving obstacles and the pairwise shape keep them in the pair's first frame.
+//   * work queue: when enough lanes have finished their trajectory the warp takes new candidates from a global
+//     counter (ballot + popc, one atomicAdd per warp). A few new candidates are built by the whole warp (one lane
+//     per axis), many by their own lanes. With host buffers the candidates may still be arriving over PCIe: a warp
+//     then waits for the copy engine's progress word.
+//   * CTA lockstep (CheckParams::lockstep, chosen per launch): one __syncthreads_count per trip keeps the warps of a
+//     CTA in the same part of the loop body and aligns their fetches -- used for short tables and the pairwise
+//     shape; tables of 16+ obstacles run with free-running warps.
 //   * per-CTA partial verdict counts / best candidate, reduced in block order by k_finalize (deterministic).
 #include "rqcd_device.cuh"
 #include "rqcd_kernels.cuh"
