@@ -330,7 +330,6 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
               if (kk < m) {
                 TableObs o;
                 o.rec = tab + (size_t)kk * p.stride;
-                o.flags = oflags[kk];
                 inside = ends_inside(o, Xs, Xf);
               }
               const unsigned bits = __ballot_sync(kFull, inside);
@@ -353,7 +352,7 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
 
     // ---- CollisionChecker::CollisionCheck entry for the lane's next obstacle (CollisionChecker.cpp:70-80);
     // its end-point tests ride on the first frame below
-    if (kEndBits && have && !in_pair) {
+    if (kEndBits && have && !in_pair && k < m && ((inbits[(k >> 5) * kThreads + tid] >> (k & 31)) & 1u)) {
       // pairs whose end-point test is positive are Collisions without a section (CollisionChecker.cpp:73-77)
       while (k < m && ((inbits[(k >> 5) * kThreads + tid] >> (k & 31)) & 1u) && !(p.early_exit && verdict != 0)) {
         if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)1;
@@ -407,7 +406,6 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
         TableObs o;
         const int kk = min(k, max(m - 1, 0));
         o.rec = tab + (size_t)kk * p.stride;
-        o.flags = oflags[kk];
         r = frame<!kEndBits>(c, ts, tf, ends, first_frame, in_pair, o, p.min_t, ch);
       }
       first_frame = false;
