@@ -412,7 +412,7 @@ def main():
         if not args.no_cpu_baseline:
             impl, kind = cpu_checker()
             threads = os.cpu_count() or 1
-            n_c = max(1024, min(n, (1 << 24) // max(pairs_per_traj, 1)))
+            n_c = max(1024, min(n, (1 << 25) // max(pairs_per_traj, 1)))  # ~1 s on 16 threads = ~16 core-seconds
             bc_c, sph_c = host_inputs(name, W, lo, n_c)
             run_cpu(impl, name, obs, m, bc_c[:, :1024].copy(), None if sph_c is None else sph_c[:, :1024].copy(), threads)
             r, dt = run_cpu(impl, name, obs, m, bc_c, sph_c, threads)
