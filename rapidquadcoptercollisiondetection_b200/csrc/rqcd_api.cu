@@ -58,6 +58,8 @@ struct rqcd_ctx {
   DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group;
   int refill_min = 0;  // RQCD_REFILL_MIN override; 0 = chosen from the obstacle count
   int lockstep = -1;   // RQCD_LOCKSTEP override (0/1); -1 = chosen from the obstacle count
+  int pool = 1;        // RQCD_POOL (0/1): k_check_pool for all-pairs checks against static tables of 16..100 obstacles
+  int phase_b_min = 32;  // RQCD_PHASE_B_MIN
   unsigned long long launches = 0;
   char last_error[512] = {0};
 };
@@ -189,10 +191,13 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   p.lockstep = ctx->lockstep >= 0 ? ctx->lockstep : ((!cc.pairwise && p.m >= 16) ? 0 : 1);
   p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (cc.pairwise ? 8 : (p.m >= 128 ? 4 : (p.m >= 16 ? 6 : 4)));
   p.work_counter = ctx->d_counter;
-  const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->stride, moving);
+  p.pool = ctx->pool;
+  p.phase_b_min = ctx->phase_b_min;
+  const bool pool = use_pool(moving, cc.pairwise, p.m, p.early_exit != 0, p.pool != 0);
+  const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->stride, moving, pool);
   if (smem > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
-  RQCD_CU(check_prepare(cc.mode, moving, cc.pairwise, p.m, smem));
-  int per_sm = check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, p.m, smem);
+  RQCD_CU(check_prepare(cc.mode, moving, cc.pairwise, p.m, smem, pool));
+  int per_sm = check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, p.m, smem, pool);
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)ctx->prop.multiProcessorCount * per_sm;
   const long long need = (p.n + kThreads - 1) / kThreads;
@@ -411,6 +416,10 @@ int rqcd_create(rqcd_ctx** out, int device) {
   if (hc && atoll(hc) > 0) ctx->chunk_override = atoll(hc);
   const char* rm = getenv("RQCD_REFILL_MIN");
   if (rm && atoi(rm) >= 1 && atoi(rm) <= 32) ctx->refill_min = atoi(rm);
+  const char* po = getenv("RQCD_POOL");
+  if (po && (po[0] == '0' || po[0] == '1') && po[1] == 0) ctx->pool = po[0] - '0';
+  const char* pb = getenv("RQCD_PHASE_B_MIN");
+  if (pb && atoi(pb) >= 1 && atoi(pb) <= 64) ctx->phase_b_min = atoi(pb);
   const char* ls = getenv("RQCD_LOCKSTEP");
   if (ls && (ls[0] == '0' || ls[0] == '1') && ls[1] == 0) ctx->lockstep = ls[0] - '0';
   *out = ctx;

@@ -60,6 +60,8 @@ struct CheckParams {
   int early_exit;
   int refill_min;          // idle lanes per warp that trigger a work-queue fetch
   int lockstep;            // 1: the warps of a CTA meet at a barrier every trip (see k_check)
+  int pool;                // 1: k_check_pool (first frames in obstacle order, pair tasks in a warp pool) where it applies
+  int phase_b_min;         // k_check_pool: tasks (pooled + running) per warp that trigger a B trip
   unsigned long long* work_counter;
   BlockPartial* partials;  // [gridDim.x]
   // streaming input (host-pointer calls): candidates [0, *progress) have arrived in `in`; null = all present.
@@ -72,12 +74,14 @@ struct CheckParams {
 
 // once per device, before any kernel that solves a cubic: the refined reciprocals of solveP3's constant divisors
 cudaError_t init_device_constants(cudaStream_t s);
-size_t check_smem_bytes(int mp, int stride, bool moving);
+size_t check_smem_bytes(int mp, int stride, bool moving, bool pool = false);
+bool use_pool(bool moving, bool pairwise, int m, bool early_exit, bool pool);
+constexpr int kPoolMaxObstacles = 100;
 // Returns the number of kernels launched (2: check + finalize) or a negative cudaError.
 cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
                          DevSummary* d_summary);
-int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem);
-cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem);  // opt in to large dynamic smem
+int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem, bool pool = false);
+cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem, bool pool = false);  // opt in to large dynamic smem
 constexpr int kEndBitsMinObstacles = 16;  // static tables at least this long: end-point tests as a pre-pass
 
 cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, int np, uint8_t* verdict, uint8_t* matrix,
