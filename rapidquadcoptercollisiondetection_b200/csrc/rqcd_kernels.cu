@@ -28,6 +28,10 @@
 //     CTA in the same part of the loop body and aligns their fetches -- used for short tables and the pairwise
 //     shape; tables of 16+ obstacles run with free-running warps.
 //   * per-CTA partial verdict counts / best candidate, reduced in block order by k_finalize (deterministic).
+//
+// k_check_pool (further down) is the kernel of ONE shape -- all pairs against a static table of 16..100 obstacles
+// -- built around the first frame of a pair: first frames in obstacle order with X(mid) evaluated once per
+// trajectory, the pairs that need a recursion as tasks in a per-warp pool; same frame(), same verdicts.
 #include "rqcd_device.cuh"
 #include "rqcd_kernels.cuh"
 

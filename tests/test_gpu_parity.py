@@ -139,6 +139,34 @@ def test_random_sets_against_oracle(ctx, oracle, n, ns, npz, seed):
     assert_close(r["summary"]["best_cost"], o["summary"]["best_cost"], what="best cost")
 
 
+def test_both_kernels_of_the_static_all_pairs_shape(oracle, monkeypatch):
+    """Static tables of 16..100 obstacles are checked by k_check_pool (first frames in obstacle order, pair tasks in a
+    warp pool); RQCD_POOL=0 selects k_check (lane-owns-trajectory, the kernel of every other shape) for them too.
+    Both must give the oracle's verdicts, first hits, counts and best candidate -- with prebuilt coefficients and
+    ragged sizes as well (a last batch of 9 candidates; a skipped prefix of the index space)."""
+    from rapidquadcoptercollisiondetection_b200.api import Context
+    specs = W.static_obstacles(201, 20, 17)
+    obs = abi.make_obstacles(specs)
+    m = len(specs)
+    n = 32 * 311 + 9
+    bc = W.synth_bc(202, 777, n)
+    o = oracle.generate_check(bc, obs, m, MIN_T, index_base=777, nthreads=8)
+    for pool in ("1", "0"):
+        monkeypatch.setenv("RQCD_POOL", pool)
+        with Context(0) as c2:
+            c2.set_obstacles(obs, m)
+            r = c2.generate_check(bc, MIN_T, index_base=777)
+            np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"])
+            np.testing.assert_array_equal(r["verdict"], o["verdict"])
+            np.testing.assert_array_equal(r["first_obstacle"], o["first_obstacle"])
+            assert r["summary"]["traj_counts"] == o["summary"]["traj_counts"]
+            assert r["summary"]["pair_counts"] == o["summary"]["pair_counts"]
+            assert r["summary"]["best_index"] == o["summary"]["best_index"]
+            rc = c2.check(o["coeffs"], bc[abi.BC_TF], MIN_T, cost=o["cost"], index_base=777)
+            np.testing.assert_array_equal(rc["verdict_matrix"], o["verdict_matrix"])
+            assert rc["summary"]["best_index"] == o["summary"]["best_index"]
+
+
 def test_edge_cases(ctx, oracle):
     """Empty batch, empty obstacle set, a one-trajectory batch, ragged strides, invalid arguments."""
     specs = W.static_obstacles(5, 2, 2)
