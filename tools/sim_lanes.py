@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""tools/sim_lanes.py [n_traj=4096] -- lane-scheduling model of the check kernels on the C3 workload, fed with the
-REAL number of CollisionCheckSection frames of every (trajectory, obstacle) pair (counted by the CPU oracle).
+"""tools/sim_lanes.py [n_traj=4096] [c3|c5] -- lane-scheduling model of the check kernels on the C3 (or C5) workload, fed
+with the REAL number of CollisionCheckSection frames of every (trajectory, obstacle) pair (counted by the CPU oracle).
 
 It answers one question for the designs discussed in DESIGN.md section 5: what fraction of the lane slots of a warp
 carries a frame? Policies:
@@ -22,11 +22,15 @@ from oracle import binding as B
 from rapidquadcoptercollisiondetection_b200 import abi, workloads as W
 
 
-def frames_per_pair(n):
+def frames_per_pair(n, workload="c3"):
     orc = B.Oracle()
-    specs = W.static_obstacles(2, 32, 32)  # the C3 table (bench.py: obs_seed 2)
+    if workload == "c5":
+        specs = W.static_obstacles(6, 128, 128)  # the C5 table (bench.py: obs_seed 6, candidates seed 5)
+        bc = W.synth_bc(5, 0, n)
+    else:
+        specs = W.static_obstacles(2, 32, 32)  # the C3 table (bench.py: obs_seed 2, candidates seed 1)
+        bc = W.synth_bc(1, 0, n)
     obs = abi.make_obstacles(specs)
-    bc = W.synth_bc(1, 0, n)
     g = orc.generate(bc)
     co = np.ascontiguousarray(g["coeffs"].T)  # n x 18
     fn = orc._f("check_one", C.c_int)
@@ -127,8 +131,9 @@ def sim_uni(fr, trigger, pool):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-    fr = frames_per_pair(n)
-    print(f"C3 sample: {n} trajectories x {fr.shape[1]} obstacles, {fr.mean():.3f} frames per pair, "
+    wl = sys.argv[2] if len(sys.argv) > 2 else "c3"
+    fr = frames_per_pair(n, wl)
+    print(f"{wl} sample: {n} trajectories x {fr.shape[1]} obstacles, {fr.mean():.3f} frames per pair, "
           f"{(fr > 1).mean() * 100:.1f} % of the pairs need more than one, max {fr.max()}")
     per_traj = np.maximum(fr - 1, 0).sum(1)
     print(f"extra frames per trajectory: mean {per_traj.mean():.1f}, median {np.median(per_traj):.0f}, "
