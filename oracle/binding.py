@@ -28,7 +28,8 @@ REF_PATH = os.path.join(HERE, "_ref", "libref.so")
 class Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in (
         "checks", "sections", "tangent_sections", "test_points", "trig", "cardano", "root_pairs",
-        "cubic_fallback", "max_depth", "sphere_checks", "prism_checks")]
+        "cubic_fallback", "max_depth", "sphere_checks", "prism_checks", "skip_first", "skip_child",
+        "child_tangent_sections")]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -266,6 +266,37 @@ static void sort_small(double* a, int n) {
   }
 }
 
+/* Statistics only (orc_stats.skip_*): are all Bernstein coefficients of D(t) = (X(t) - pp).pn on [ts, tf] positive?
+ * D in powers of t, Taylor shift to ts, scale by h = tf - ts, power basis -> Bernstein basis of degree 5. */
+static int bernstein_positive(const double* coef, double ts, double tf, v3 pp, v3 pn) {
+  static const double binom5[6] = {1, 5, 10, 10, 5, 1};
+  static const double binom[6][6] = {{1, 0, 0, 0, 0, 0}, {1, 1, 0, 0, 0, 0}, {1, 2, 1, 0, 0, 0},
+                                     {1, 3, 3, 1, 0, 0}, {1, 4, 6, 4, 1, 0}, {1, 5, 10, 10, 5, 1}};
+  double a[6], b[6];
+  for (int j = 0; j < 6; j++) { /* a[j]: coefficient of t^j */
+    const double* c = coef + 3 * (5 - j);
+    a[j] = pn.x * c[0] + pn.y * c[1] + pn.z * c[2];
+  }
+  a[0] -= v3_dot(pp, pn);
+  const double h = tf - ts;
+  double hp = 1.0;
+  for (int j = 0; j < 6; j++) {
+    double s = 0.0, tp = 1.0;
+    for (int k = j; k < 6; k++) {
+      s += binom[k][j] * a[k] * tp;
+      tp *= ts;
+    }
+    b[j] = s * hp;
+    hp *= h;
+  }
+  for (int i = 0; i < 6; i++) {
+    double beta = 0.0;
+    for (int j = 0; j <= i; j++) beta += binom[i][j] / binom5[j] * b[j];
+    if (!(beta > 1e-9)) return 0;
+  }
+  return 1;
+}
+
 /* CollisionChecker::CollisionCheckSection -- src/CollisionChecker.cpp:82-193. */
 static int check_section(const double* coef, double ts, double tf, const prep_obs* obs, double minT,
                          orc_stats* st, int depth) {
@@ -279,7 +310,13 @@ static int check_section(const double* coef, double ts, double tf, const prep_ob
   if (tf - ts < minT) return RQCD_INDETERMINABLE;       /* :93-96 */
   v3 pp, pn;
   tangent_plane(obs, midpoint, &pp, &pn); /* :99 */
-  if (st) st->tangent_sections++;
+  if (st) {
+    st->tangent_sections++;
+    if (depth > 1) st->child_tangent_sections++;
+    if (bernstein_positive(coef, ts, tf, pp, pn)) {
+      if (depth > 1) st->skip_child++; else st->skip_first++;
+    }
+  }
 
   /* :103-111 with Trajectory::GetDerivativeCoeffs (Trajectory.hpp:105-112) */
   double c[5] = {0, 0, 0, 0, 0};
@@ -578,6 +615,9 @@ static void stats_add(orc_stats* a, const orc_stats* b) {
   if (b->max_depth > a->max_depth) a->max_depth = b->max_depth;
   a->sphere_checks += b->sphere_checks;
   a->prism_checks += b->prism_checks;
+  a->skip_first += b->skip_first;
+  a->skip_child += b->skip_child;
+  a->child_tangent_sections += b->child_tangent_sections;
 }
 
 static void* run_shard(void* arg) {

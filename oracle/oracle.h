@@ -33,6 +33,11 @@ typedef struct orc_stats {
   uint64_t cubic_fallback;   /* |c0| <= 1e-6 branch (CollisionChecker.cpp:119-120) */
   uint64_t max_depth;        /* deepest recursion seen */
   uint64_t sphere_checks, prism_checks;
+  /* statistics for the certified solver skip of the CUDA path: tangent sections whose scalar quintic
+   * D(t) = (X(t) - point).normal has all six Bernstein coefficients on [ts, tf] positive -- there every plane-side test
+   * of the reference is negative whatever the roots are, so the section is NoCollision without the root solver. Counted
+   * apart for a pair's first section and for deeper ones. Statistics only: no verdict depends on them. */
+  uint64_t skip_first, skip_child, child_tangent_sections;
 } orc_stats;
 
 /* Quartic::solveP3 / solve_quartic (src/quartic.cpp:39-72, 77-156). */
