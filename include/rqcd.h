@@ -180,6 +180,9 @@ int rqcd_synchronize(rqcd_ctx* ctx);
 int rqcd_read_summary(rqcd_ctx* ctx, rqcd_summary* out);
 /* Number of kernels this context has launched since creation. */
 uint64_t rqcd_launch_count(const rqcd_ctx* ctx);
+/* Name of the check kernel of the most recent rqcd_generate_check / rqcd_check / rqcd_generate_check_pairwise /
+ * rqcd_plan_best launch on this context ("" before the first): what a profile of the call must show. */
+const char* rqcd_last_kernel_name(const rqcd_ctx* ctx);
 
 /* Replaces constructing Sphere / RectPrism objects and the vector<shared_ptr<ConvexObj>> the drivers
  * hold (ForestPerformanceEval.cpp:130-150). Host pointer always. Rotation matrices and half sides are

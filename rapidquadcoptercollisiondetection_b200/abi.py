@@ -118,6 +118,7 @@ SYMBOLS = {
     "rqcd_synchronize": (C.c_int, [_VP]),
     "rqcd_read_summary": (C.c_int, [_VP, C.POINTER(Summary)]),
     "rqcd_launch_count": (C.c_uint64, [_VP]),
+    "rqcd_last_kernel_name": (C.c_char_p, [_VP]),
     "rqcd_set_obstacles": (C.c_int, [_VP, C.POINTER(Obstacle), C.c_int32]),
     "rqcd_num_obstacles": (C.c_int32, [_VP]),
     "rqcd_generate": (C.c_int, [_VP, C.POINTER(BcSoa), C.c_int64, C.c_uint32, C.POINTER(Out)]),

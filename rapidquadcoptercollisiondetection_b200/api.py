@@ -82,6 +82,9 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.rqcd_launch_count(self.h))
 
+    def last_kernel_name(self) -> str:
+        return (self.lib.rqcd_last_kernel_name(self.h) or b"").decode()
+
     def read_summary(self) -> dict:
         s = abi.Summary()
         self._chk(self.lib.rqcd_read_summary(self.h, C.byref(s)), allow=(abi.ERR_DEPTH_CAP,))

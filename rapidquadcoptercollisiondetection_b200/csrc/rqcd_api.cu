@@ -58,8 +58,10 @@ struct rqcd_ctx {
   DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group;
   int refill_min = 0;  // RQCD_REFILL_MIN override; 0 = chosen from the obstacle count
   int lockstep = -1;   // RQCD_LOCKSTEP override (0/1); -1 = chosen from the obstacle count
-  int pool = 1;        // RQCD_POOL (0/1): k_check_pool for all-pairs checks against static tables of 16..100 obstacles
-  int phase_b_min = 32;  // RQCD_PHASE_B_MIN
+  int pool = 1;        // RQCD_POOL (0/1): k_pool (staged sections, certified solver skip) for obstacle tables
+  int th_solve = 24, th_plane = 20;  // RQCD_TH_SOLVE / RQCD_TH_PLANE: see CheckParams
+  long long stream_timeout = 1ll << 32;  // RQCD_STREAM_TIMEOUT_CYCLES (~2 s): a streamed chunk that never arrives fails the call
+  const char* last_kernel = "";  // name of the check kernel of the most recent launch (rqcd_last_kernel_name)
   unsigned long long launches = 0;
   char last_error[512] = {0};
 };
@@ -182,32 +184,58 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   p.m = cc.pairwise ? 1 : ctx->m;
   p.mp = ctx->mp;
   p.stride = ctx->stride;
-  // CTA lockstep or free-running warps, and the idle lanes per warp that trigger a work-queue fetch (in lockstep:
-  // the CTA's average): a fetch costs a pass in which only the fetching lanes (and, for a few of them, the helpers
-  // that build their axes) work, an idle lane costs a slot in every frame until then. Measured optima on B200
-  // (final build): tables of 16+ obstacles run free (C3 +7 %, C4 +3 %, C5 +4 % over lockstep) and fetch at 6 idle
-  // lanes (4 from 128 obstacles on); the Forest shape (5 obstacles, early exit) and the pairwise shape, whose
-  // warps fetch every other trip, stay in lockstep (which also aligns their fetches) at 4 and 8.
-  p.lockstep = ctx->lockstep >= 0 ? ctx->lockstep : ((!cc.pairwise && p.m >= 16) ? 0 : 1);
-  p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (cc.pairwise ? 8 : (p.m >= 128 ? 4 : (p.m >= 16 ? 6 : 4)));
   p.work_counter = ctx->d_counter;
-  p.pool = ctx->pool;
-  p.phase_b_min = ctx->phase_b_min;
-  const bool pool = use_pool(moving, cc.pairwise, p.m, p.early_exit != 0, p.pool != 0);
-  const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->stride, moving, pool);
-  if (smem > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
-  RQCD_CU(check_prepare(cc.mode, moving, cc.pairwise, p.m, smem, pool));
-  int per_sm = check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, p.m, smem, pool);
-  if (per_sm < 1) per_sm = 1;
-  long long grid = (long long)ctx->prop.multiProcessorCount * per_sm;
-  const long long need = (p.n + kThreads - 1) / kThreads;
-  if (grid > need) grid = need;
-  if (grid < 1) grid = 1;
-  int st = ensure_partials(ctx, (int)grid);
-  if (st != RQCD_OK) return st;
-  p.partials = ctx->d_partials;
-  RQCD_CU(launch_check(p, cc.mode, moving, cc.pairwise, (int)grid, ctx->stream, ctx->d_summary));
-  ctx->launches += 2;  // k_check + k_finalize
+  p.stream_timeout = ctx->stream_timeout;
+  const int sms = ctx->prop.multiProcessorCount;
+  // ---- which kernel: obstacle tables go to k_pool (staged sections with the certified solver skip) when the table
+  // fits beside the trajectory rows; the pairwise shape, empty tables and oversized tables go to k_check
+  int pool_t = 0;
+  if (ctx->pool && !cc.pairwise && p.m >= 1 && p.m < 65536)
+    pool_t = pool_threads(ctx->mp, ctx->stride, ctx->prop.sharedMemPerMultiprocessor, kMaxSmem);
+  long long grid;
+  if (pool_t > 0) {
+    p.th_solve = ctx->th_solve;
+    p.th_plane = ctx->th_plane;
+    const size_t smem = pool_smem_bytes(ctx->mp, ctx->stride, pool_t);
+    RQCD_CU(pool_prepare(cc.mode, moving, pool_t, smem));
+    int per_sm = pool_max_blocks_per_sm(cc.mode, moving, pool_t, smem);
+    if (per_sm < 1) per_sm = 1;
+    grid = (long long)sms * per_sm;
+    const long long need = (p.n + pool_t - 1) / pool_t;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    int st = ensure_partials(ctx, (int)grid);
+    if (st != RQCD_OK) return st;
+    p.partials = ctx->d_partials;
+    RQCD_CU(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), ctx->stream));
+    RQCD_CU(launch_pool(p, cc.mode, moving, pool_t, (int)grid, smem, ctx->stream));
+    ctx->last_kernel = pool_kernel_name(moving);
+  } else {
+    // CTA lockstep or free-running warps, and the idle lanes per warp that trigger a work-queue fetch (in lockstep:
+    // the CTA's average): a fetch costs a pass in which only the fetching lanes (and, for a few of them, the helpers
+    // that build their axes) work, an idle lane costs a slot in every frame until then. Measured optima on B200:
+    // tables of 16+ obstacles run free and fetch at 6 idle lanes (4 from 128 obstacles on); short tables and the
+    // pairwise shape, whose warps fetch every other trip, stay in lockstep (which also aligns their fetches) at 4 and 8.
+    p.lockstep = ctx->lockstep >= 0 ? ctx->lockstep : ((!cc.pairwise && p.m >= 16) ? 0 : 1);
+    p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (cc.pairwise ? 8 : (p.m >= 128 ? 4 : (p.m >= 16 ? 6 : 4)));
+    const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->stride, moving);
+    if (smem > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
+    RQCD_CU(check_prepare(cc.mode, moving, cc.pairwise, p.m, smem));
+    int per_sm = check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, p.m, smem);
+    if (per_sm < 1) per_sm = 1;
+    grid = (long long)sms * per_sm;
+    const long long need = (p.n + kThreads - 1) / kThreads;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    int st = ensure_partials(ctx, (int)grid);
+    if (st != RQCD_OK) return st;
+    p.partials = ctx->d_partials;
+    RQCD_CU(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), ctx->stream));
+    RQCD_CU(launch_check(p, cc.mode, moving, cc.pairwise, (int)grid, ctx->stream));
+    ctx->last_kernel = check_kernel_name(moving, cc.pairwise, p.m);
+  }
+  RQCD_CU(launch_finalize(ctx->d_partials, (int)grid, ctx->d_summary, ctx->stream));
+  ctx->launches += 2;  // the check kernel + k_finalize
   ctx->summary_valid = true;
   return RQCD_OK;
 }
@@ -317,9 +345,15 @@ int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long lo
     ctx->h_stream[ci] = (unsigned long long)c1;
     return cudaMemcpyAsync(ctx->d_stream, ctx->h_stream + ci, sizeof(unsigned long long), cudaMemcpyHostToDevice, hs);
   };
+  // Every chunk copy and progress update is enqueued BEFORE the kernel is launched: the copies are asynchronous and
+  // ordered on the copy stream, the compute stream only waits for the first chunk. After its launch the kernel never
+  // depends on further host progress, so a blocking or serialised launch (CUDA_LAUNCH_BLOCKING, a profiler's kernel
+  // replay, a descheduled host thread) cannot turn a valid call into a time-out.
   const long long first_end = chunk < n ? chunk : n;
   RQCD_CU(copy_chunk(0, 0, first_end));
   RQCD_CU(cudaEventRecord(ctx->ev_in, hs));
+  int ci = 1;
+  for (long long c0 = first_end; c0 < n; c0 += chunk, ci++) RQCD_CU(copy_chunk(ci, c0, c0 + chunk < n ? c0 + chunk : n));
   RQCD_CU(cudaStreamWaitEvent(cs, ctx->ev_in, 0));
   cc.p.progress = ctx->d_stream;
   cc.p.stream_error = ctx->d_stream + 1;
@@ -327,8 +361,6 @@ int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long lo
   cc.p.progress = nullptr;
   cc.p.stream_error = nullptr;
   if (st != RQCD_OK) return st;
-  int ci = 1;
-  for (long long c0 = first_end; c0 < n; c0 += chunk, ci++) RQCD_CU(copy_chunk(ci, c0, c0 + chunk < n ? c0 + chunk : n));
   if (n > 0) {
     if (o.verdict) RQCD_CU(cudaMemcpyAsync(out->verdict, o.verdict, (size_t)n, cudaMemcpyDeviceToHost, cs));
     if (o.first) RQCD_CU(cudaMemcpyAsync(out->first_obstacle, o.first, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
@@ -407,6 +439,7 @@ int rqcd_create(rqcd_ctx** out, int device) {
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stream, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_stream, (kMaxChunks + 1) * sizeof(unsigned long long));
   if (e == cudaSuccess) e = init_device_constants(ctx->own_stream);
+  if (e == cudaSuccess) e = init_pool_constants(ctx->own_stream);
   if (e != cudaSuccess) {
     rqcd_destroy(ctx);
     return RQCD_ERR_CUDA;
@@ -418,8 +451,12 @@ int rqcd_create(rqcd_ctx** out, int device) {
   if (rm && atoi(rm) >= 1 && atoi(rm) <= 32) ctx->refill_min = atoi(rm);
   const char* po = getenv("RQCD_POOL");
   if (po && (po[0] == '0' || po[0] == '1') && po[1] == 0) ctx->pool = po[0] - '0';
-  const char* pb = getenv("RQCD_PHASE_B_MIN");
-  if (pb && atoi(pb) >= 1 && atoi(pb) <= 64) ctx->phase_b_min = atoi(pb);
+  const char* th = getenv("RQCD_TH_SOLVE");
+  if (th && atoi(th) >= 1 && atoi(th) <= 32) ctx->th_solve = atoi(th);
+  th = getenv("RQCD_TH_PLANE");
+  if (th && atoi(th) >= 1 && atoi(th) <= 32) ctx->th_plane = atoi(th);
+  const char* to = getenv("RQCD_STREAM_TIMEOUT_CYCLES");
+  if (to && atoll(to) > 0) ctx->stream_timeout = atoll(to);
   const char* ls = getenv("RQCD_LOCKSTEP");
   if (ls && (ls[0] == '0' || ls[0] == '1') && ls[1] == 0) ctx->lockstep = ls[0] - '0';
   *out = ctx;
@@ -497,6 +534,8 @@ int rqcd_read_summary(rqcd_ctx* ctx, rqcd_summary* out) {
 
 uint64_t rqcd_launch_count(const rqcd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+const char* rqcd_last_kernel_name(const rqcd_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
+
 int rqcd_set_obstacles(rqcd_ctx* ctx, const rqcd_obstacle* obstacles, int32_t m) {
   if (!ctx || m < 0 || (m > 0 && !obstacles)) return RQCD_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
@@ -508,7 +547,8 @@ int rqcd_set_obstacles(rqcd_ctx* ctx, const rqcd_obstacle* obstacles, int32_t m)
   }
   const int stride = (any_moving ? OF_MOVING_FIELDS : OF_STATIC_FIELDS) | 1;  // odd: bank spread, see rqcd_device.cuh
   const int mp = (m + 3) / 4 * 4;
-  if (check_smem_bytes(mp, stride, any_moving) > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
+  if (check_smem_bytes(mp, stride, any_moving) > kMaxSmem && pool_threads(mp, stride, kMaxSmem, kMaxSmem) == 0)
+    return RQCD_ERR_UNSUPPORTED;
   const size_t bytes = (size_t)stride * mp * 8 + (size_t)mp * 4;
   std::vector<unsigned char> blob(bytes > 0 ? bytes : 16, 0);
   double* tab = reinterpret_cast<double*>(blob.data());

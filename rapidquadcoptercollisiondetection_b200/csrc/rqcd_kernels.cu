@@ -32,90 +32,18 @@
 // k_check_pool (further down) is the kernel of ONE shape -- all pairs against a static table of 16..100 obstacles
 // -- built around the first frame of a pair: first frames in obstacle order with X(mid) evaluated once per
 // trajectory, the pairs that need a recursion as tasks in a per-warp pool; same frame(), same verdicts.
-#include "rqcd_device.cuh"
-#include "rqcd_kernels.cuh"
+#include "rqcd_kernel_util.cuh"
 
 namespace rqcd {
 
 namespace {
 
-constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCoopOwners = 10;  // new candidates a warp builds cooperatively in one pass (3 lanes each)
-
-
-// ---- TMA bulk copy global -> shared (1-D), completion on an mbarrier ---------------------------------
-RQCD_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-RQCD_DEV void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-RQCD_DEV void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-RQCD_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "RQCD_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra RQCD_DONE;\n"
-      "bra RQCD_WAIT;\n"
-      "RQCD_DONE:\n"
-      "}\n" ::"r"(smem_addr(bar)),
-      "r"(parity)
-      : "memory");
-}
 
 // Per-trajectory constants (window, cost) are read once per obstacle: they live in a volatile per-thread local
 // array (L1-resident), not in registers.
 enum TrajRow { SLOT_T0 = 0, SLOT_T1, SLOT_COST, kTrajRows };
 constexpr int kSlotRows = EndPoints::kRows;  // per-thread shared-memory rows
-
-RQCD_DEV bool better(double ca, long long ia, double cb, long long ib) {
-  // candidate a beats b: lower cost, or equal cost and lower index; an empty slot has index -1
-  if (ia < 0) return false;
-  if (ib < 0) return true;
-  return ca < cb || (ca == cb && ia < ib);
-}
-
-// Inputs are read once and may still be arriving over PCIe while the kernel runs (CheckParams::progress): load
-// them at L2 (ld.global.cg), the coherence point with the copy engine, never through a possibly stale L1 line.
-RQCD_DEV double ld_in(const double* p) { return __ldcg(p); }
-
-// ---- trajectory construction for one lane ------------------------------------------------------------
-template <int MODE>
-RQCD_DEV void load_trajectory(const CheckParams& p, long long i, double (&c)[18], double& t0, double& t1,
-                              double& cost) {
-  if (MODE == MODE_BC) {
-    const double* d = p.in;
-    const long long s = p.in_stride;
-    const double Tf = ld_in(d + 18 * s + i);
-    double total = 0.0;
-#pragma unroll
-    for (int ax = 0; ax < 3; ax++) {
-      const double p0 = ld_in(d + (0 + ax) * s + i), v0 = ld_in(d + (3 + ax) * s + i), a0 = ld_in(d + (6 + ax) * s + i);
-      const double pf = ld_in(d + (9 + ax) * s + i), vf = ld_in(d + (12 + ax) * s + i), af = ld_in(d + (15 + ax) * s + i);
-      const AxisParams q = gen_axis(p0, v0, a0, pf, vf, af, (p.goal_mask >> (3 * ax)) & 1,
-                                    (p.goal_mask >> (3 * ax + 1)) & 1, (p.goal_mask >> (3 * ax + 2)) & 1, Tf);
-      axis_coeffs(q, p0, v0, a0, c[0 + ax], c[3 + ax], c[6 + ax], c[9 + ax], c[12 + ax], c[15 + ax]);
-      total = (ax == 0) ? q.cost : total + q.cost;  // GetCost: cost[0] + cost[1] + cost[2] (.hpp:214-216)
-    }
-    cost = total;
-    t0 = 0.0;
-    t1 = Tf;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 18; j++) c[j] = ld_in(p.in + j * p.in_stride + i);
-    t0 = p.t_start ? ld_in(p.t_start + i) : 0.0;
-    t1 = ld_in(p.t_end + i);
-    cost = p.cost_in ? ld_in(p.cost_in + i) : __longlong_as_double(0x7ff8000000000000ll);
-  }
-}
 
 #ifdef RQCD_MAXNREG  // kernel-variant experiments: an explicit register cap instead of a resident-CTA target
 #define RQCD_CHECK_BOUNDS __maxnreg__(RQCD_MAXNREG)
@@ -199,20 +127,8 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
         if (p.progress) {  // streaming input: wait until the copy engine has delivered everything this warp took
           unsigned long long want = b + (unsigned long long)cnt;
           if (want > (unsigned long long)p.n) want = (unsigned long long)p.n;
-          if (want > avail) {
-            const long long t_begin = clock64();
-            for (;;) {
-              avail = *reinterpret_cast<const volatile unsigned long long*>(p.progress);
-              if (avail >= want) break;
-              if (clock64() - t_begin > (1ll << 32)) {  // ~2 s: the copy never came; fail the call instead of hanging
-                if (lane == 0) atomicExch(p.stream_error, 1ull);
-                arrived = false;
-                exhausted = true;
-                break;
-              }
-              __nanosleep(256);
-            }
-          }
+          arrived = wait_for_input(p, want, avail, lane);
+          if (!arrived) exhausted = true;
         }
         bool fresh = false;
         const long long my_i = (long long)b + __popc(need & lt_mask);
@@ -513,336 +429,6 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
   }
 }
 
-
-// ---------------------------------------------------------------------------------------------------------------
-// k_check_pool: all pairs against a static table of 16..~100 obstacles, organised around the FIRST frame of a pair
-// (80 % of all frames; DESIGN.md section 5, "the first-frame experiment"). A warp takes 32 candidates at a time.
-//   * A trip: every lane takes the first frame of (its trajectory, obstacle k), k the same for the whole warp: the
-//     midpoint of a first frame is the middle of the whole window, so X(mid) is evaluated ONCE per trajectory and
-//     read from the lane's row; every lane carries a frame. A pair that needs children becomes a TASK in the warp's
-//     pool in shared memory: (owner lane, obstacle, high child start, low child end).
-//   * B trip, taken when enough tasks are around (or the table is through): a free lane pops a task, runs the pair's
-//     recursion on it -- depth first, low children parked on its private stack, exactly k_check's state machine --
-//     with the OWNER's coefficients read from the owner's shared-memory rows, and reports a verdict other than
-//     NoCollision to the owner (atomicMin on (obstacle << 2 | verdict): the trajectory's verdict is the one of the
-//     lowest obstacle index, ForestPerformanceEval.cpp:216-225).
-//   * both kinds of trip run the SAME frame body (frame_at; "X(mid) given" is a warp-uniform choice), so the loop
-//     has one body in the instruction cache.
-//   * when the table is through, the pool is empty and no lane holds a task, the 32 trajectories are finished.
-constexpr int kPoolCap = 64;                  // tasks per warp; an A trip adds at most 32
-constexpr int kPoolHigh = kPoolCap - 32;
-enum PoolRow { PR_X0 = 0, PR_X1 = 3, PR_AMAX = 6, PR_XM = 7, PR_T0 = 10, PR_T1 = 11, PR_C = 12, kPoolRows = 30 };
-static_assert(PR_AMAX == 6 && EndPoints::kRows == 7, "rows 0..6 are read through EndPoints");
-
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, RQCD_MIN_BLOCKS) k_check_pool(const CheckParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int kWarps = kThreads / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wbase = tid - lane;
-  const int m = p.m, mp = p.mp;
-  double* tab = reinterpret_cast<double*>(smem_raw);
-  int* oflags = reinterpret_cast<int*>(tab + (size_t)p.stride * mp);
-  unsigned long long* wcnt = reinterpret_cast<unsigned long long*>(oflags + mp);      // [kWarps][8]
-  double* bcost = reinterpret_cast<double*>(wcnt + kWarps * 8);                       // [kThreads]
-  long long* bidx = reinterpret_cast<long long*>(bcost + kThreads);                   // [kThreads]
-  double* rows = reinterpret_cast<double*>(bidx + kThreads);                          // [kPoolRows][kThreads]
-  long long* idx_row = reinterpret_cast<long long*>(rows + kPoolRows * kThreads);     // [kThreads]
-  double2* pool_ab = reinterpret_cast<double2*>(idx_row + kThreads);                  // [kWarps][kPoolCap]
-  int* pool_ok = reinterpret_cast<int*>(pool_ab + kWarps * kPoolCap);                 // [kWarps][kPoolCap]: owner << 16 | k
-  unsigned* res = reinterpret_cast<unsigned*>(pool_ok + kWarps * kPoolCap);           // [kThreads]: min (k << 2 | verdict)
-  unsigned* inbits = res + kThreads;                                                  // [(mp + 31) / 32][kThreads]
-  __shared__ __align__(8) uint64_t mbar;
-
-  const uint32_t blob_bytes = (uint32_t)(((size_t)p.stride * mp) * 8 + (size_t)mp * 4);
-  if (tid == 0) mbar_init(&mbar, 1);
-  if (tid < kWarps * 8) wcnt[tid] = 0ull;
-  bcost[tid] = __longlong_as_double(0x7ff0000000000000ll);
-  bidx[tid] = -1;
-#pragma unroll
-  for (int j = 0; j < kPoolRows; j++) rows[j * kThreads + tid] = 0.0;
-  __syncthreads();
-  if (blob_bytes > 0) {
-    if (tid == 0) tma_bulk_g2s(tab, p.obs_blob, blob_bytes, &mbar);
-    mbar_wait(&mbar, 0);
-  }
-  (void)oflags;
-
-  double c[18];
-#pragma unroll
-  for (int j = 0; j < 18; j++) c[j] = 0.0;
-  double* my_row = rows + tid;
-  double2* wpool_ab = pool_ab + warp * kPoolCap;
-  int* wpool_ok = pool_ok + warp * kPoolCap;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  double2 stack[kMaxDepth];  // the running task's parked low children {ts, lo_tf}
-  unsigned long long avail = 0;
-  bool exhausted = false;
-  const double nan = __longlong_as_double(0x7ff8000000000000ll);
-
-  while (!exhausted) {
-    // ---- a batch of 32 candidates
-    unsigned long long b = 0;
-    if (lane == 0) b = atomicAdd(p.work_counter, 32ull);
-    b = __shfl_sync(kFull, b, 0);
-    if (b >= (unsigned long long)p.n) break;
-    if (b + 32ull >= (unsigned long long)p.n) exhausted = true;
-    if (p.progress) {  // streaming input: wait until the copy engine has delivered the whole batch
-      unsigned long long want = b + 32ull;
-      if (want > (unsigned long long)p.n) want = (unsigned long long)p.n;
-      bool arrived = true;
-      if (want > avail) {
-        const long long t_begin = clock64();
-        for (;;) {
-          avail = *reinterpret_cast<const volatile unsigned long long*>(p.progress);
-          if (avail >= want) break;
-          if (clock64() - t_begin > (1ll << 32)) {  // ~2 s: the copy never came; fail the call instead of hanging
-            if (lane == 0) atomicExch(p.stream_error, 1ull);
-            arrived = false;
-            break;
-          }
-          __nanosleep(256);
-        }
-      }
-      if (!arrived) break;
-    }
-    const long long idx = (long long)b + lane;
-    const bool have = idx < p.n && !(p.skip && p.skip[idx] != 0);  // planner: dropped by an earlier stage
-    double t0 = 0.0, t1 = 0.0, cost = 0.0;
-    if (have) {
-      load_trajectory<MODE>(p, idx, c, t0, t1, cost);
-      if (MODE == MODE_BC) {
-        if (p.cost) p.cost[idx] = cost;
-        if (p.coeffs) {
-#pragma unroll
-          for (int j = 0; j < 18; j++) p.coeffs[j * p.coeff_stride + idx] = c[j];
-        }
-      }
-      const V3 x0 = traj_value(c, t0), x1 = traj_value(c, t1);
-      const V3 xm = traj_value(c, (t0 + t1) / 2);  // the first frame's midpoint (CollisionChecker.cpp:87), every obstacle
-      my_row[(PR_X0 + 0) * kThreads] = x0.x, my_row[(PR_X0 + 1) * kThreads] = x0.y, my_row[(PR_X0 + 2) * kThreads] = x0.z;
-      my_row[(PR_X1 + 0) * kThreads] = x1.x, my_row[(PR_X1 + 1) * kThreads] = x1.y, my_row[(PR_X1 + 2) * kThreads] = x1.z;
-      my_row[PR_AMAX * kThreads] = side_filter_bound(c, t0, t1);
-      my_row[(PR_XM + 0) * kThreads] = xm.x, my_row[(PR_XM + 1) * kThreads] = xm.y, my_row[(PR_XM + 2) * kThreads] = xm.z;
-      my_row[PR_T0 * kThreads] = t0;
-      my_row[PR_T1 * kThreads] = t1;
-#pragma unroll
-      for (int j = 0; j < 18; j++) my_row[(PR_C + j) * kThreads] = c[j];
-    }
-    idx_row[tid] = idx;
-    res[tid] = 0xffffffffu;
-    {
-      // CollisionCheck's end-point tests (CollisionChecker.cpp:73-77) against the whole table, by the whole warp
-      unsigned todo = __ballot_sync(kFull, have);
-      __syncwarp();
-      while (todo) {
-        const int owner = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const double* row = rows + (wbase + owner);
-        const V3 Xs = v3(row[0], row[kThreads], row[2 * kThreads]);
-        const V3 Xf = v3(row[3 * kThreads], row[4 * kThreads], row[5 * kThreads]);
-        for (int k0 = 0; k0 < m; k0 += 32) {
-          const int kk = k0 + lane;
-          bool inside = false;
-          if (kk < m) {
-            TableObs o;
-            o.rec = tab + (size_t)kk * p.stride;
-            inside = ends_inside(o, Xs, Xf);
-          }
-          const unsigned bits = __ballot_sync(kFull, inside);
-          if (lane == owner) inbits[(k0 >> 5) * kThreads + tid] = bits;
-        }
-      }
-      __syncwarp();
-    }
-
-    // ---- the batch. Lane state of a running task (B trips): owner, obstacle, interval, parked low children.
-    bool task = false;
-    int owner = lane, kk = 0, sp = 0, pool_n = 0, k = 0;
-    double ts = 0.0, tf = 0.0;
-    unsigned n1 = 0, n2 = 0, n3 = 0;  // pairs this lane decided as Collision / Indeterminable / depth cap
-    bool own_c = true;                 // the lane's registers hold its own trajectory's coefficients
-    for (;;) {
-      const int n_busy = __popc(__ballot_sync(kFull, task));
-      const bool phase_a = k < m && pool_n <= kPoolHigh && (pool_n + n_busy) < p.phase_b_min;
-      if (!phase_a && pool_n + n_busy == 0) break;
-      // ---- set the frame up
-      double f_ts, f_tf, f_mid;
-      V3 f_xm;
-      int f_k;
-      bool active;
-      const double* orow;  // the rows of the trajectory this lane's frame belongs to
-      if (phase_a) {
-        if (!__all_sync(kFull, own_c)) {  // a B trip replaced them
-#pragma unroll
-          for (int j = 0; j < 18; j++) c[j] = my_row[(PR_C + j) * kThreads];
-          own_c = true;
-        }
-        const bool bit = (inbits[(k >> 5) * kThreads + tid] >> (k & 31)) & 1u;
-        active = have & !bit;
-        if (have & bit) {  // an end point of the trajectory is inside: Collision without a section (:73-77)
-          if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)1;
-          n1++;
-          atomicMin(&res[tid], ((unsigned)k << 2) | 1u);
-        }
-        orow = my_row;
-        f_ts = t0, f_tf = t1, f_k = k;
-        f_mid = (t0 + t1) / 2;
-        f_xm = v3(my_row[(PR_XM + 0) * kThreads], my_row[(PR_XM + 1) * kThreads], my_row[(PR_XM + 2) * kThreads]);
-      } else {
-        // free lanes take tasks from the top of the pool
-        const unsigned free_m = __ballot_sync(kFull, !task);
-        const int rank = __popc(free_m & lt_mask);
-        if (!task && rank < pool_n) {
-          const int slot = pool_n - 1 - rank;
-          const double2 ab = wpool_ab[slot];
-          const int ok = wpool_ok[slot];
-          owner = ok >> 16;
-          kk = ok & 0xffff;
-          const double* r_ = rows + (wbase + owner);
-          const double o_t0 = r_[PR_T0 * kThreads], o_t1 = r_[PR_T1 * kThreads];
-          const bool has_hi = ab.x == ab.x, has_lo = ab.y == ab.y;
-          sp = 0;
-          if (has_hi) {
-            ts = ab.x, tf = o_t1;
-            if (has_lo) stack[sp++] = make_double2(o_t0, ab.y);  // the low child waits until the high subtree is clear
-          } else {
-            ts = o_t0, tf = ab.y;
-          }
-          task = true;
-        }
-        pool_n -= min(__popc(free_m), pool_n);
-        __syncwarp();
-        orow = rows + (wbase + owner);
-#pragma unroll
-        for (int j = 0; j < 18; j++) c[j] = orow[(PR_C + j) * kThreads];
-        own_c = owner == lane;
-        active = task;
-        f_ts = ts, f_tf = tf, f_k = kk;
-        f_mid = (ts + tf) / 2;
-        f_xm = traj_value(c, f_mid);
-      }
-      EndPoints ends;
-      ends.slot = const_cast<double*>(orow);
-      ends.stride = kThreads;
-      TableObs o;
-      o.rec = tab + (size_t)f_k * p.stride;
-      Children ch;
-      const int r = frame_at<false>(c, f_ts, f_tf, f_mid, f_xm, ends, false, active, o, p.min_t, ch);
-
-      if (phase_a) {
-        // ---- a first frame: decided, or a task for the pool
-        const bool spawn = active & (r == STEP_CHILD);
-        const unsigned spawn_m = __ballot_sync(kFull, spawn);
-        if (active) {
-          if (spawn) {
-            if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)0;  // until the task says otherwise
-            const int slot = pool_n + __popc(spawn_m & lt_mask);
-            const double hi_start = ch.has_hi ? ch.t_next : nan;
-            const double lo_end = ch.has_lo ? (ch.has_hi ? ch.lo_tf : ch.t_next) : nan;
-            wpool_ab[slot] = make_double2(hi_start, lo_end);
-            wpool_ok[slot] = (lane << 16) | k;
-          } else {
-            if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)(r == STEP_CLEAR ? 0 : r);
-            if (r != STEP_CLEAR) {
-              n1 += (r == 1), n2 += (r == 2);
-              atomicMin(&res[tid], ((unsigned)k << 2) | (unsigned)r);
-            }
-          }
-        }
-        pool_n += __popc(spawn_m);
-        __syncwarp();
-        k++;
-      } else if (task) {
-        // ---- a frame of a running task: k_check's state update
-        int pv = -1;
-        if (r == STEP_CHILD) {
-          if (ch.has_hi & ch.has_lo) {
-            if (sp < kMaxDepth) stack[sp++] = make_double2(ts, ch.lo_tf);
-            else pv = 3;  // deeper than RQCD_MAX_DEPTH: never silent truncation
-          }
-          if (ch.has_hi) ts = ch.t_next;
-          else tf = ch.t_next;
-        } else if (r == STEP_CLEAR) {
-          if (sp > 0) {
-            const double2 e = stack[--sp];
-            ts = e.x, tf = e.y;
-          } else {
-            pv = 0;
-          }
-        } else {
-          pv = r;
-        }
-        if (pv >= 0) {
-          task = false;
-          if (pv != 0) {
-            n1 += (pv == 1), n2 += (pv == 2), n3 += (pv == 3);
-            atomicMin(&res[wbase + owner], ((unsigned)kk << 2) | (unsigned)pv);
-            if (p.verdict_matrix) p.verdict_matrix[idx_row[wbase + owner] * (long long)m + kk] = (uint8_t)pv;
-          }
-        }
-      }
-    }
-
-    // ---- the batch is through: counters per warp, verdicts per owner
-    __syncwarp();
-    const unsigned word = res[tid];
-    const int verdict = (have && word != 0xffffffffu) ? (int)(word & 3u) : 0;
-    const int first = (have && word != 0xffffffffu) ? (int)(word >> 2) : -1;
-    const unsigned s1 = __reduce_add_sync(kFull, n1), s2 = __reduce_add_sync(kFull, n2), s3 = __reduce_add_sync(kFull, n3);
-    const int tv = have ? verdict : -1;
-    const unsigned q0 = __ballot_sync(kFull, tv == 0), q1 = __ballot_sync(kFull, tv == 1);
-    const unsigned q2 = __ballot_sync(kFull, tv == 2), q3 = __ballot_sync(kFull, tv == 3);
-    if (lane == 0) {
-      unsigned long long* w = wcnt + warp * 8;
-      const unsigned n_traj = __popc(q0) + __popc(q1) + __popc(q2) + __popc(q3);
-      w[0] += __popc(q0), w[1] += __popc(q1), w[2] += __popc(q2), w[3] += __popc(q3);
-      w[4] += (unsigned long long)n_traj * (unsigned)m - s1 - s2 - s3;
-      w[5] += s1, w[6] += s2, w[7] += s3;
-    }
-    if (have) {
-      if (p.verdict) p.verdict[idx] = (uint8_t)verdict;
-      if (p.first_obstacle) p.first_obstacle[idx] = first;
-      if (verdict == 0 && cost < bcost[tid]) {  // indices handed to one lane ascend, so ties keep the lowest
-        bcost[tid] = cost;
-        bidx[tid] = p.index_base + idx;
-      }
-    }
-    __syncwarp();
-  }
-
-  // ---- CTA partial
-  __syncthreads();
-  if (tid < 32) {
-    double bc = __longlong_as_double(0x7ff0000000000000ll);
-    long long bi = -1;
-    for (int j = lane; j < kThreads; j += 32) {
-      if (better(bcost[j], bidx[j], bc, bi)) {
-        bc = bcost[j];
-        bi = bidx[j];
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double oc = __shfl_down_sync(kFull, bc, off);
-      const long long oi = __shfl_down_sync(kFull, bi, off);
-      if (better(oc, oi, bc, bi)) {
-        bc = oc;
-        bi = oi;
-      }
-    }
-    BlockPartial* out = p.partials + blockIdx.x;
-    if (lane < 8) {
-      unsigned long long sum = 0;
-      for (int w = 0; w < kWarps; w++) sum += wcnt[w * 8 + lane];
-      if (lane < 4) out->traj[lane] = sum;
-      else out->pair[lane - 4] = sum;
-    }
-    if (lane == 0) {
-      out->best_cost = bc;
-      out->best_index = bi;
-    }
-  }
-}
 
 __global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int nparts, DevSummary* out) {
   __shared__ unsigned long long cnt[8];
@@ -1166,9 +752,7 @@ const void* check_fn() {
 // cheaper inside the pairs' first frames.
 bool use_endbits(bool moving, bool pairwise, int m) { return !moving && !pairwise && m >= kEndBitsMinObstacles; }
 
-const void* select_check(int mode, bool moving, bool pairwise, int m, bool pool = false) {
-  if (pool) return mode == MODE_BC ? reinterpret_cast<const void*>(&k_check_pool<MODE_BC>)
-                                   : reinterpret_cast<const void*>(&k_check_pool<MODE_COEFF>);
+const void* select_check(int mode, bool moving, bool pairwise, int m) {
   if (pairwise) return check_fn<MODE_BC, false, true, false>();
   if (moving) return mode == MODE_BC ? check_fn<MODE_BC, true, false, false>() : check_fn<MODE_COEFF, true, false, false>();
   if (use_endbits(moving, pairwise, m))
@@ -1185,12 +769,6 @@ int grid_for(long long n, int cap) {
 
 }  // namespace
 
-// k_check_pool applies to all-pairs checks against static tables that are long enough for the end-point pre-pass
-// and short enough for two CTAs beside the trajectory rows.
-bool use_pool(bool moving, bool pairwise, int m, bool early_exit, bool pool) {
-  return pool && use_endbits(moving, pairwise, m) && !early_exit && m <= kPoolMaxObstacles;
-}
-
 cudaError_t init_device_constants(cudaStream_t s) {
   k_init_constants<<<1, 1, 0, s>>>();
   cudaError_t e = cudaGetLastError();
@@ -1203,15 +781,7 @@ cudaError_t init_device_constants(cudaStream_t s) {
   return cudaStreamSynchronize(s);
 }
 
-size_t check_smem_bytes(int mp, int stride, bool moving, bool pool) {
-  if (pool) {
-    size_t u = (size_t)stride * mp * 8 + (size_t)mp * 4;                  // table + flags
-    u += (kThreads / 32) * 8 * 8 + (size_t)kThreads * 16;                 // warp counters, best cost / index
-    u += (size_t)kThreads * 8 * kPoolRows + (size_t)kThreads * 8;         // trajectory rows, global indices
-    u += (size_t)(kThreads / 32) * kPoolCap * (16 + 4);                   // task pools
-    u += (size_t)kThreads * 4 + (size_t)((mp + 31) / 32) * kThreads * 4;  // verdict words, end-point bits
-    return u;
-  }
+size_t check_smem_bytes(int mp, int stride, bool moving) {
   size_t b = (size_t)stride * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
   b += (size_t)8 * kThreads * 8;                          // verdict counters, one row of 8 per thread
   b += (size_t)kThreads * 16;                             // best cost / index per thread
@@ -1221,34 +791,38 @@ size_t check_smem_bytes(int mp, int stride, bool moving, bool pool) {
   return b;
 }
 
-cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem, bool pool) {
-  return cudaFuncSetAttribute(select_check(mode, moving, pairwise, m, pool), cudaFuncAttributeMaxDynamicSharedMemorySize,
+cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem) {
+  return cudaFuncSetAttribute(select_check(mode, moving, pairwise, m), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)smem);
 }
 
-int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem, bool pool) {
+int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, select_check(mode, moving, pairwise, m, pool), kThreads, smem) !=
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, select_check(mode, moving, pairwise, m), kThreads, smem) !=
       cudaSuccess)
     return 0;
   return nb;
 }
 
-cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
-                         DevSummary* d_summary) {
-  const bool pool = use_pool(moving, pairwise, p.m, p.early_exit != 0, p.pool != 0);
-  const size_t smem = check_smem_bytes(pairwise ? 0 : p.mp, pairwise ? 0 : p.stride, moving, pool);
-  cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
-  if (e != cudaSuccess) return e;
+const char* check_kernel_name(bool moving, bool pairwise, int m) {
+  if (pairwise) return "k_check<pairwise>";
+  if (moving) return "k_check<moving>";
+  return use_endbits(moving, pairwise, m) ? "k_check<static,endbits>" : "k_check<static>";
+}
+
+cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s) {
+  const size_t smem = check_smem_bytes(pairwise ? 0 : p.mp, pairwise ? 0 : p.stride, moving);
   CheckParams q = p;
   if (pairwise) {
     q.mp = 0;
     q.stride = 0;
   }
   void* args[] = {&q};
-  e = cudaLaunchKernel(select_check(mode, moving, pairwise, p.m, pool), dim3(grid), dim3(kThreads), args, smem, s);
-  if (e != cudaSuccess) return e;
-  k_finalize<<<1, 256, 0, s>>>(p.partials, grid, d_summary);
+  return cudaLaunchKernel(select_check(mode, moving, pairwise, p.m), dim3(grid), dim3(kThreads), args, smem, s);
+}
+
+cudaError_t launch_finalize(const BlockPartial* partials, int grid, DevSummary* d_summary, cudaStream_t s) {
+  k_finalize<<<1, 256, 0, s>>>(partials, grid, d_summary);
   return cudaGetLastError();
 }
 

@@ -60,29 +60,39 @@ struct CheckParams {
   int early_exit;
   int refill_min;          // idle lanes per warp that trigger a work-queue fetch
   int lockstep;            // 1: the warps of a CTA meet at a barrier every trip (see k_check)
-  int pool;                // 1: k_check_pool (first frames in obstacle order, pair tasks in a warp pool) where it applies
-  int phase_b_min;         // k_check_pool: tasks (pooled + running) per warp that trigger a B trip
+  int th_solve, th_plane;  // k_pool: lanes waiting for the solver / plane stage that trigger that kind of trip
   unsigned long long* work_counter;
   BlockPartial* partials;  // [gridDim.x]
   // streaming input (host-pointer calls): candidates [0, *progress) have arrived in `in`; null = all present.
   // The copy engine advances *progress after each chunk; *stream_error is set if a wait times out.
   const unsigned long long* progress;
   unsigned long long* stream_error;
+  long long stream_timeout;  // SM cycles a warp waits for a chunk before it fails the call
   // planner: candidates with skip[i] != 0 were rejected by an earlier stage and are not checked (nor counted)
   const uint8_t* skip;
 };
 
 // once per device, before any kernel that solves a cubic: the refined reciprocals of solveP3's constant divisors
+// (one copy per kernel translation unit)
 cudaError_t init_device_constants(cudaStream_t s);
-size_t check_smem_bytes(int mp, int stride, bool moving, bool pool = false);
-bool use_pool(bool moving, bool pairwise, int m, bool early_exit, bool pool);
-constexpr int kPoolMaxObstacles = 100;
-// Returns the number of kernels launched (2: check + finalize) or a negative cudaError.
-cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s,
-                         DevSummary* d_summary);
-int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem, bool pool = false);
-cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem, bool pool = false);  // opt in to large dynamic smem
+cudaError_t init_pool_constants(cudaStream_t s);
+
+// ---- k_check (rqcd_kernels.cu): lane owns trajectory; every shape
+size_t check_smem_bytes(int mp, int stride, bool moving);
+cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s);
+int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem);
+cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem);  // opt in to large dynamic smem
+const char* check_kernel_name(bool moving, bool pairwise, int m);
 constexpr int kEndBitsMinObstacles = 16;  // static tables at least this long: end-point tests as a pre-pass
+cudaError_t launch_finalize(const BlockPartial* partials, int grid, DevSummary* d_summary, cudaStream_t s);
+
+// ---- k_pool (rqcd_pool.cu): staged sections with the certified solver skip; obstacle tables, static or moving
+size_t pool_smem_bytes(int mp, int stride, int threads);
+int pool_threads(int mp, int stride, size_t smem_per_sm, size_t smem_per_block_max);  // 256 / 384 / 512, 0 = does not fit
+cudaError_t pool_prepare(int mode, bool moving, int threads, size_t smem);
+int pool_max_blocks_per_sm(int mode, bool moving, int threads, size_t smem);
+cudaError_t launch_pool(const CheckParams& p, int mode, bool moving, int threads, int grid, size_t smem, cudaStream_t s);
+const char* pool_kernel_name(bool moving);
 
 cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, int np, uint8_t* verdict, uint8_t* matrix,
                           cudaStream_t s);

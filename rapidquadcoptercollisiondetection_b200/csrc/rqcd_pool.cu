@@ -1,0 +1,491 @@
+// rqcd_pool.cu -- k_pool, the staged check kernel for obstacle TABLES (static or moving), sm_100a. Compile with
+// -fmad=false (see rqcd_device.cuh). Same verdicts as k_check (rqcd_kernels.cu), which stays the kernel of the
+// pairwise shape and of tables that do not fit next to the trajectory rows.
+//
+// The reference's CollisionCheckSection (src/CollisionChecker.cpp:82-193) is cut into two STAGES:
+//   PLANE stage   X(mid), IsPointInside(mid), the tf - ts < minT test, GetTangentPlane(mid) (:87-99) and the certified
+//                 solver skip (bernstein_clear, rqcd_device.cuh): when the plane-side quintic is positive on the whole
+//                 interval, no test point of the reference can be on the obstacle side, whatever the roots are, and the
+//                 section is NoCollision without children. 80 % of first sections and 50 % of deeper ones end here.
+//   SOLVE stage   the rest (:103-191): critical times (quartic / cubic), sort, classification, plane-side tests, children.
+// A warp works on 32 candidates at a time (its batch; their coefficients sit in per-thread shared-memory rows so that
+// any lane can work for any trajectory) and chooses one of three kinds of TRIP, each one converged instruction stream:
+//   A trip   every lane runs the PLANE stage of the first section of (its own trajectory, obstacle k), k the same for the
+//            whole warp: obstacle record = broadcast loads, X(mid) of the whole window read from the row (evaluated once
+//            per trajectory). Pairs that need the solver become TASKS in the warp's pool: (owner lane, obstacle, plane).
+//   S trip   lanes holding a task in state NEED_SOLVE run the SOLVE stage; a section with children continues on the same
+//            lane in state NEED_PLANE (depth first, the low child parked on the lane's private stack -- the reference's
+//            recursion order); idle lanes first take tasks from the pool.
+//   P trip   lanes in state NEED_PLANE run the PLANE stage of their child section.
+// A trip of one kind is taken when enough lanes wait for it (CheckParams::th_solve / th_plane), A trips fill the gaps,
+// so that every trip runs with most of its lanes busy although only 1 section in 4 needs the solver.
+// A verdict other than NoCollision goes to the owner with one shared-memory atomicMin on (obstacle << 2 | verdict): the
+// trajectory's verdict is the one of the lowest obstacle index (test/ForestPerformanceEval.cpp:216-225). With
+// RQCD_F_EARLY_EXIT tasks and first sections of obstacles behind a known hit are dropped, and the executed-pair counts
+// are the driver's (pairs up to and including the first hit).
+#include "rqcd_kernel_util.cuh"
+
+namespace rqcd {
+
+namespace {
+
+constexpr int kPoolCap = 64;  // tasks per warp; an A trip adds at most 32 and is only taken when 32 slots are free
+// per-thread shared-memory rows
+enum PoolRow {
+  PR_XM = 0,    // X(mid of the whole window): the first section's midpoint, the same for every obstacle (static tables)
+  PR_T0 = 3, PR_T1 = 4,
+  PR_AMAX = 5,  // side_filter_bound of the trajectory (static tables)
+  PR_C = 6,     // 18 coefficients
+  PR_PL = 24,   // plane (point, normal) of the task this LANE is running, between its PLANE and SOLVE stages
+  kPoolRows = 30
+};
+enum LaneState { LS_IDLE = 0, LS_NEED_PLANE = 1, LS_NEED_SOLVE = 2 };
+enum PlaneStage { PS_CLEAR = 0, PS_COLLISION = 1, PS_INDETERM = 2, PS_SOLVE = 4 };
+
+// The PLANE stage of one section (CollisionChecker.cpp:89-99 + the certified skip). All 32 lanes call it together.
+template <class Obs>
+RQCD_DEV int plane_stage(const double (&c)[18], const Obs& obs, V3 Xm, double ts, double tf, double amax, double minT,
+                         bool active, V3& pp, V3& pn) {
+  const V3 ctr = obs.center();
+  const double rad = obs.radius();
+  const bool prism = obs.prism();
+  bool in_m;
+  {
+    FastMath f;
+    tangent_plane(f, obs, Xm, ctr, rad, prism, in_m, pp, pn);
+    if (!warp_all(f.ok | !active)) {
+      PlainMath pm;
+      tangent_plane(pm, obs, Xm, ctr, rad, prism, in_m, pp, pn);
+    }
+  }
+  const bool clear = bernstein_clear(c, pp, pn, ts, tf, amax);
+  int r = clear ? PS_CLEAR : PS_SOLVE;
+  r = (tf - ts < minT) ? PS_INDETERM : r;  // :93-96
+  r = in_m ? PS_COLLISION : r;             // :89-92
+  return r;
+}
+
+template <int MODE, bool MOVING, int T>
+__global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kWarps = T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wbase = tid - lane;
+  const int m = p.m, mp = p.mp;
+  double* tab = reinterpret_cast<double*>(smem_raw);
+  int* oflags = reinterpret_cast<int*>(tab + (size_t)p.stride * mp);
+  unsigned long long* wcnt = reinterpret_cast<unsigned long long*>(oflags + mp);      // [kWarps][8]
+  double* bcost = reinterpret_cast<double*>(wcnt + kWarps * 8);                       // [T]
+  long long* bidx = reinterpret_cast<long long*>(bcost + T);                          // [T]
+  double* rows = reinterpret_cast<double*>(bidx + T);                                 // [kPoolRows][T]
+  long long* idx_row = reinterpret_cast<long long*>(rows + kPoolRows * T);            // [T]
+  double* pool_pl = reinterpret_cast<double*>(idx_row + T);                           // [kWarps][6][kPoolCap]: planes
+  int* pool_ok = reinterpret_cast<int*>(pool_pl + kWarps * 6 * kPoolCap);             // [kWarps][kPoolCap]: owner << 16 | k
+  unsigned* res = reinterpret_cast<unsigned*>(pool_ok + kWarps * kPoolCap);           // [T]: min (k << 2 | verdict)
+  unsigned* inbits = res + T;                                                         // [(mp + 31) / 32][T], static tables
+  __shared__ __align__(8) uint64_t mbar;
+
+  const uint32_t blob_bytes = (uint32_t)(((size_t)p.stride * mp) * 8 + (size_t)mp * 4);
+  if (tid == 0) mbar_init(&mbar, 1);
+  if (tid < kWarps * 8) wcnt[tid] = 0ull;
+  bcost[tid] = __longlong_as_double(0x7ff0000000000000ll);
+  bidx[tid] = -1;
+#pragma unroll
+  for (int j = 0; j < kPoolRows; j++) rows[j * T + tid] = (j == PR_PL + 3) ? 1.0 : 0.0;  // a harmless plane for idle lanes
+  __syncthreads();
+  if (blob_bytes > 0) {
+    if (tid == 0) tma_bulk_g2s(tab, p.obs_blob, blob_bytes, &mbar);
+    mbar_wait(&mbar, 0);
+  }
+
+  double c[18];
+#pragma unroll
+  for (int j = 0; j < 18; j++) c[j] = 0.0;
+  double* my_row = rows + tid;
+  double* wpool_pl = pool_pl + warp * 6 * kPoolCap;
+  int* wpool_ok = pool_ok + warp * kPoolCap;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  double2 stack[kMaxDepth];  // the running task's parked low children {ts, lo_tf}
+  unsigned long long avail = 0;
+  bool exhausted = false;
+  const bool early = p.early_exit != 0;
+
+  while (!exhausted) {
+    // ---- a batch of 32 candidates
+    unsigned long long b = 0;
+    if (lane == 0) b = atomicAdd(p.work_counter, 32ull);
+    b = __shfl_sync(kFull, b, 0);
+    if (b >= (unsigned long long)p.n) break;
+    if (b + 32ull >= (unsigned long long)p.n) exhausted = true;
+    if (p.progress) {  // streaming input: wait until the copy engine has delivered the whole batch
+      unsigned long long want = b + 32ull;
+      if (want > (unsigned long long)p.n) want = (unsigned long long)p.n;
+      if (!wait_for_input(p, want, avail, lane)) break;
+    }
+    const long long idx = (long long)b + lane;
+    const bool have = idx < p.n && !(p.skip && p.skip[idx] != 0);  // planner: dropped by an earlier stage
+    double t0 = 0.0, t1 = 0.0, cost = 0.0;
+    V3 x0 = v3(0, 0, 0), x1 = v3(0, 0, 0);
+    if (have) {
+      load_trajectory<MODE>(p, idx, c, t0, t1, cost);
+      if (MODE == MODE_BC) {
+        if (p.cost) p.cost[idx] = cost;
+        if (p.coeffs) {
+#pragma unroll
+          for (int j = 0; j < 18; j++) p.coeffs[j * p.coeff_stride + idx] = c[j];
+        }
+      }
+      if (!MOVING) {
+        x0 = traj_value(c, t0), x1 = traj_value(c, t1);
+        const V3 xm = traj_value(c, (t0 + t1) / 2);  // the first section's midpoint (CollisionChecker.cpp:87), every obstacle
+        my_row[(PR_XM + 0) * T] = xm.x, my_row[(PR_XM + 1) * T] = xm.y, my_row[(PR_XM + 2) * T] = xm.z;
+        my_row[PR_AMAX * T] = side_filter_bound(c, t0, t1);
+      }
+      my_row[PR_T0 * T] = t0;
+      my_row[PR_T1 * T] = t1;
+#pragma unroll
+      for (int j = 0; j < 18; j++) my_row[(PR_C + j) * T] = c[j];
+    }
+    idx_row[tid] = idx;
+    res[tid] = 0xffffffffu;
+    if (!MOVING) {
+      // CollisionCheck's end-point tests (CollisionChecker.cpp:73-77) against the whole table: lane = trajectory, the
+      // obstacle record is a broadcast load; bit k of the lane's words = an end point is inside obstacle k
+      for (int k0 = 0; k0 < m; k0 += 32) {
+        unsigned bits = 0;
+        const int kend = min(32, m - k0);
+        for (int j = 0; j < kend; j++) {
+          TableObs o;
+          o.rec = tab + (size_t)(k0 + j) * p.stride;
+          bits |= ends_inside(o, x0, x1) ? (1u << j) : 0u;
+        }
+        inbits[(k0 >> 5) * T + tid] = have ? bits : 0u;
+      }
+    }
+    __syncwarp();
+
+    // ---- the batch. Lane state of a running task: owner, obstacle, interval, parked low children.
+    int st = LS_IDLE, owner = lane, kk = 0, sp = 0, pool_n = 0, k = 0;
+    double ts = 0.0, tf = 0.0;
+    unsigned n1 = 0, n2 = 0, n3 = 0;  // pairs this lane decided as Collision / Indeterminable / depth cap (all-pairs mode)
+    for (;;) {
+      // early exit: a task of an obstacle behind the owner's known first hit is moot
+      if (early && st != LS_IDLE && (res[wbase + owner] >> 2) < (unsigned)kk) st = LS_IDLE;
+      // ---- idle lanes take tasks from the top of the pool; a pooled task has its plane and waits for the solver
+      {
+        const unsigned idle_m = __ballot_sync(kFull, st == LS_IDLE);
+        const int take_n = min(__popc(idle_m), pool_n);
+        if (take_n > 0) {
+          const int rank = __popc(idle_m & lt_mask);
+          if (st == LS_IDLE && rank < take_n) {
+            const int slot = pool_n - 1 - rank;
+            const int ok = wpool_ok[slot];
+            owner = ok >> 16;
+            kk = ok & 0xffff;
+#pragma unroll
+            for (int j = 0; j < 6; j++) my_row[(PR_PL + j) * T] = wpool_pl[j * kPoolCap + slot];
+            const double* r_ = rows + (wbase + owner);
+            ts = r_[PR_T0 * T], tf = r_[PR_T1 * T];
+            if (MOVING && (oflags[kk] & OBS_MOVING)) {
+              const double* rec = tab + (size_t)kk * p.stride;
+              const double ms = rec[OF_MT0], me = rec[OF_MT1];
+              ts = (ts < ms) ? ms : ts;  // std::max(_startTime, rhs start), Trajectory.hpp:121-128
+              tf = (me < tf) ? me : tf;  // std::min(_endTime, rhs end)
+            }
+            sp = 0;
+            st = LS_NEED_SOLVE;
+          }
+          pool_n -= take_n;
+          __syncwarp();
+        }
+      }
+      const int n_plane = __popc(__ballot_sync(kFull, st == LS_NEED_PLANE));
+      const int n_solve = __popc(__ballot_sync(kFull, st == LS_NEED_SOLVE));
+      const bool a_ok = k < m && pool_n <= kPoolCap - 32;
+      int trip;  // 0: A, 1: P, 2: S
+      if (n_solve >= p.th_solve) trip = 2;
+      else if (n_plane >= p.th_plane) trip = 1;
+      else if (a_ok) trip = 0;
+      else if (n_solve > 0 && n_solve >= n_plane) trip = 2;
+      else if (n_plane > 0) trip = 1;
+      else break;  // table through, pool empty, no lane holds a task: the batch is done
+
+      int pv = -1;  // verdict of the task that ended in this trip, if any
+      if (trip == 0) {
+        // ---- A trip: the PLANE stage of the first section of (own trajectory, obstacle k)
+#pragma unroll
+        for (int j = 0; j < 18; j++) c[j] = my_row[(PR_C + j) * T];
+        const double* rec = tab + (size_t)k * p.stride;
+        bool active = have && !(early && (res[tid] >> 2) < (unsigned)k);
+        double a_ts = t0, a_tf = t1, amax;
+        V3 xm;
+        int pre = -1;  // decided before the section: 1 an end point is inside, 0 no common window
+        if (!MOVING) {
+          const bool bit = (inbits[(k >> 5) * T + tid] >> (k & 31)) & 1u;
+          if (active & bit) pre = 1;  // Collision without a section (:73-77)
+          xm = v3(my_row[(PR_XM + 0) * T], my_row[(PR_XM + 1) * T], my_row[(PR_XM + 2) * T]);
+          amax = my_row[PR_AMAX * T];
+        } else {
+          TableObs o;
+          o.rec = rec;
+          if (oflags[k] & OBS_MOVING) {  // warp-uniform
+            // Trajectory::operator- (Trajectory.hpp:121-128): coefficient-wise difference on the common window
+#pragma unroll
+            for (int j = 0; j < 18; j++) c[j] = c[j] - rec[OF_MOTION + j];
+            const double ms = rec[OF_MT0], me = rec[OF_MT1];
+            a_ts = (t0 < ms) ? ms : t0;
+            a_tf = (me < t1) ? me : t1;
+            if (active & !(a_ts <= a_tf)) pre = 0;  // no common time (the reference would assert, Trajectory.hpp:68)
+          }
+          const bool in_ends = ends_inside(o, traj_value(c, a_ts), traj_value(c, a_tf));
+          __syncwarp();
+          if (active & (pre < 0) & in_ends) pre = 1;
+          xm = traj_value(c, (a_ts + a_tf) / 2);
+          amax = side_filter_bound(c, a_ts, a_tf);
+        }
+        active = active & (pre < 0);
+        TableObs o;
+        o.rec = rec;
+        V3 pp, pn;
+        const int r = plane_stage(c, o, xm, a_ts, a_tf, amax, p.min_t, active, pp, pn);
+        const bool spawn = active & (r == PS_SOLVE);
+        const unsigned spawn_m = __ballot_sync(kFull, spawn);
+        if (spawn) {
+          const int slot = pool_n + __popc(spawn_m & lt_mask);
+          wpool_ok[slot] = (lane << 16) | k;
+          wpool_pl[0 * kPoolCap + slot] = pp.x, wpool_pl[1 * kPoolCap + slot] = pp.y, wpool_pl[2 * kPoolCap + slot] = pp.z;
+          wpool_pl[3 * kPoolCap + slot] = pn.x, wpool_pl[4 * kPoolCap + slot] = pn.y, wpool_pl[5 * kPoolCap + slot] = pn.z;
+        }
+        const int v = (pre >= 0) ? pre : (active ? (r & 3) : -1);  // PS_SOLVE & 3 == 0: NoCollision until the task says otherwise
+        if (v >= 0) {
+          if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)v;
+          if (v != 0) {
+            n1 += (v == 1), n2 += (v == 2);
+            atomicMin(&res[tid], ((unsigned)k << 2) | (unsigned)v);
+          }
+        }
+        pool_n += __popc(spawn_m);
+        __syncwarp();
+        k++;
+        continue;
+      }
+
+      // ---- P and S trips work on the lanes' tasks: the owner's coefficients (relative to a moving obstacle)
+      const double* orow = rows + (wbase + owner);
+#pragma unroll
+      for (int j = 0; j < 18; j++) c[j] = orow[(PR_C + j) * T];
+      const double* rec = tab + (size_t)kk * p.stride;
+      if (MOVING) {
+#pragma unroll
+        for (int j = 0; j < 18; j++) c[j] = c[j] - rec[OF_MOTION + j];  // zeros for a static obstacle of the table
+      }
+      const double amax = MOVING ? side_filter_bound(c, ts, tf) : orow[PR_AMAX * T];
+      const double mid = (ts + tf) / 2;  // :87
+      if (trip == 1) {
+        // ---- P trip: the PLANE stage of a child section
+        const bool act = st == LS_NEED_PLANE;
+        TableObs o;
+        o.rec = rec;
+        V3 pp, pn;
+        const int r = plane_stage(c, o, traj_value(c, mid), ts, tf, amax, p.min_t, act, pp, pn);
+        if (act) {
+          if (r == PS_SOLVE) {
+            my_row[(PR_PL + 0) * T] = pp.x, my_row[(PR_PL + 1) * T] = pp.y, my_row[(PR_PL + 2) * T] = pp.z;
+            my_row[(PR_PL + 3) * T] = pn.x, my_row[(PR_PL + 4) * T] = pn.y, my_row[(PR_PL + 5) * T] = pn.z;
+            st = LS_NEED_SOLVE;
+          } else if (r == PS_CLEAR && sp > 0) {  // subtree clear: resume the innermost parked low child
+            const double2 e = stack[--sp];
+            ts = e.x, tf = e.y;
+          } else {
+            pv = r;  // NoCollision with nothing parked, Collision or Indeterminable: the pair is done
+          }
+        }
+      } else {
+        // ---- S trip: the SOLVE stage
+        const bool act = st == LS_NEED_SOLVE;
+        const V3 pp = v3(my_row[(PR_PL + 0) * T], my_row[(PR_PL + 1) * T], my_row[(PR_PL + 2) * T]);
+        const V3 pn = v3(my_row[(PR_PL + 3) * T], my_row[(PR_PL + 4) * T], my_row[(PR_PL + 5) * T]);
+        double pc[5], r0, r1, r2, r3;
+        int n;
+        {
+          FastMath f;
+          n = critical_times(f, c, pn, pc, r0, r1, r2, r3);
+          if (!warp_all(f.ok | !act)) {
+            PlainMath pm;
+            n = critical_times(pm, c, pn, pc, r0, r1, r2, r3);
+          }
+        }
+        Children ch;
+        section_children(c, ts, tf, mid, pp, pn, pc, n, r0, r1, r2, r3, amax, act, ch);
+        if (act) {
+          if (ch.has_hi | ch.has_lo) {
+            if (ch.has_hi & ch.has_lo) {  // the parent's low tail call waits until the high subtree is clear
+              if (sp < kMaxDepth) stack[sp++] = make_double2(ts, ch.lo_tf);
+              else pv = 3;  // deeper than RQCD_MAX_DEPTH: never silent truncation
+            }
+            if (ch.has_hi) ts = ch.t_next;
+            else tf = ch.t_next;
+            st = LS_NEED_PLANE;
+          } else if (sp > 0) {
+            const double2 e = stack[--sp];
+            ts = e.x, tf = e.y;
+            st = LS_NEED_PLANE;
+          } else {
+            pv = 0;
+          }
+        }
+      }
+      if (pv >= 0) {
+        st = LS_IDLE;
+        if (pv != 0) {
+          n1 += (pv == 1), n2 += (pv == 2), n3 += (pv == 3);
+          atomicMin(&res[wbase + owner], ((unsigned)kk << 2) | (unsigned)pv);
+          if (p.verdict_matrix) p.verdict_matrix[idx_row[wbase + owner] * (long long)m + kk] = (uint8_t)pv;
+        }
+      }
+    }
+
+    // ---- the batch is through: counters per warp, verdicts per owner
+    __syncwarp();
+    const unsigned word = res[tid];
+    const bool hit = have && word != 0xffffffffu;
+    const int verdict = hit ? (int)(word & 3u) : 0;
+    const int first = hit ? (int)(word >> 2) : -1;
+    unsigned c0;  // NoCollision pairs of this lane's trajectory
+    if (early) {  // the driver's loop stops at the first hit: pairs behind it were not executed
+      n1 = verdict == 1, n2 = verdict == 2, n3 = verdict == 3;
+      c0 = have ? (hit ? (unsigned)first : (unsigned)m) : 0u;
+    } else {
+      c0 = have ? (unsigned)m : 0u;  // minus the s1 + s2 + s3 below
+    }
+    const unsigned s0 = __reduce_add_sync(kFull, c0);
+    const unsigned s1 = __reduce_add_sync(kFull, n1), s2 = __reduce_add_sync(kFull, n2), s3 = __reduce_add_sync(kFull, n3);
+    const int tv = have ? verdict : -1;
+    const unsigned q0 = __ballot_sync(kFull, tv == 0), q1 = __ballot_sync(kFull, tv == 1);
+    const unsigned q2 = __ballot_sync(kFull, tv == 2), q3 = __ballot_sync(kFull, tv == 3);
+    if (lane == 0) {
+      unsigned long long* w = wcnt + warp * 8;
+      w[0] += __popc(q0), w[1] += __popc(q1), w[2] += __popc(q2), w[3] += __popc(q3);
+      w[4] += early ? s0 : s0 - s1 - s2 - s3;
+      w[5] += s1, w[6] += s2, w[7] += s3;
+    }
+    if (have) {
+      if (p.verdict) p.verdict[idx] = (uint8_t)verdict;
+      if (p.first_obstacle) p.first_obstacle[idx] = first;
+      if (verdict == 0 && cost < bcost[tid]) {  // indices handed to one lane ascend, so ties keep the lowest
+        bcost[tid] = cost;
+        bidx[tid] = p.index_base + idx;
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- CTA partial
+  __syncthreads();
+  if (tid < 32) {
+    double bc = __longlong_as_double(0x7ff0000000000000ll);
+    long long bi = -1;
+    for (int j = lane; j < T; j += 32) {
+      if (better(bcost[j], bidx[j], bc, bi)) {
+        bc = bcost[j];
+        bi = bidx[j];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double oc = __shfl_down_sync(kFull, bc, off);
+      const long long oi = __shfl_down_sync(kFull, bi, off);
+      if (better(oc, oi, bc, bi)) {
+        bc = oc;
+        bi = oi;
+      }
+    }
+    BlockPartial* out = p.partials + blockIdx.x;
+    if (lane < 8) {
+      unsigned long long sum = 0;
+      for (int w = 0; w < kWarps; w++) sum += wcnt[w * 8 + lane];
+      if (lane < 4) out->traj[lane] = sum;
+      else out->pair[lane - 4] = sum;
+    }
+    if (lane == 0) {
+      out->best_cost = bc;
+      out->best_index = bi;
+    }
+  }
+}
+
+__device__ double g_pool_rcp_const[3];
+__global__ void k_pool_init_constants() {
+  g_pool_rcp_const[0] = rcp_refined(3.0);
+  g_pool_rcp_const[1] = rcp_refined(9.0);
+  g_pool_rcp_const[2] = rcp_refined(54.0);
+}
+
+template <int T>
+const void* pool_fn(int mode, bool moving) {
+  if (moving)
+    return mode == MODE_BC ? reinterpret_cast<const void*>(&k_pool<MODE_BC, true, T>)
+                           : reinterpret_cast<const void*>(&k_pool<MODE_COEFF, true, T>);
+  return mode == MODE_BC ? reinterpret_cast<const void*>(&k_pool<MODE_BC, false, T>)
+                         : reinterpret_cast<const void*>(&k_pool<MODE_COEFF, false, T>);
+}
+const void* pool_fn(int mode, bool moving, int threads) {
+  if (threads == 256) return pool_fn<256>(mode, moving);
+  if (threads == 384) return pool_fn<384>(mode, moving);
+  return pool_fn<512>(mode, moving);
+}
+
+}  // namespace
+
+// this translation unit's copy of the refined reciprocals of solveP3's constant divisors (see init_device_constants)
+cudaError_t init_pool_constants(cudaStream_t s) {
+  k_pool_init_constants<<<1, 1, 0, s>>>();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  void* src = nullptr;
+  e = cudaGetSymbolAddress(&src, g_pool_rcp_const);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbolAsync(kRcpConst, src, sizeof(double) * 3, 0, cudaMemcpyDeviceToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);
+}
+
+size_t pool_smem_bytes(int mp, int stride, int threads) {
+  const size_t T = (size_t)threads, W = T / 32;
+  size_t u = (size_t)stride * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
+  u += W * 8 * 8 + T * 16;                              // warp counters, best cost / index
+  u += T * 8 * kPoolRows + T * 8;                       // trajectory rows, global indices
+  u += W * kPoolCap * (6 * 8 + 4);                      // task pools: planes, owner/obstacle words
+  u += T * 4 + (size_t)((mp + 31) / 32) * T * 4;        // verdict words, end-point bits
+  return u;
+}
+
+// CTA size for a table: two CTAs of 256 threads per SM when their shared memory fits twice, else one CTA of 512 or
+// 384 threads (the table is then shared by all warps of the SM). 0: the table does not fit beside the rows.
+int pool_threads(int mp, int stride, size_t smem_per_sm, size_t smem_per_block_max) {
+  const size_t reserve = 1024;  // per resident CTA
+  if (2 * (pool_smem_bytes(mp, stride, 256) + reserve) <= smem_per_sm) return 256;
+  if (pool_smem_bytes(mp, stride, 512) <= smem_per_block_max) return 512;
+  if (pool_smem_bytes(mp, stride, 384) <= smem_per_block_max) return 384;
+  if (pool_smem_bytes(mp, stride, 256) <= smem_per_block_max) return 256;
+  return 0;
+}
+
+const char* pool_kernel_name(bool moving) { return moving ? "k_pool<moving>" : "k_pool<static>"; }
+
+cudaError_t pool_prepare(int mode, bool moving, int threads, size_t smem) {
+  return cudaFuncSetAttribute(pool_fn(mode, moving, threads), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+int pool_max_blocks_per_sm(int mode, bool moving, int threads, size_t smem) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pool_fn(mode, moving, threads), threads, smem) != cudaSuccess) return 0;
+  return nb;
+}
+
+cudaError_t launch_pool(const CheckParams& p, int mode, bool moving, int threads, int grid, size_t smem, cudaStream_t s) {
+  CheckParams q = p;
+  void* args[] = {&q};
+  return cudaLaunchKernel(pool_fn(mode, moving, threads), dim3(grid), dim3(threads), args, smem, s);
+}
+
+}  // namespace rqcd

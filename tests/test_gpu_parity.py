@@ -140,10 +140,10 @@ def test_random_sets_against_oracle(ctx, oracle, n, ns, npz, seed):
 
 
 def test_both_kernels_of_the_static_all_pairs_shape(oracle, monkeypatch):
-    """Static tables of 16..100 obstacles are checked by k_check_pool (first frames in obstacle order, pair tasks in a
-    warp pool); RQCD_POOL=0 selects k_check (lane-owns-trajectory, the kernel of every other shape) for them too.
-    Both must give the oracle's verdicts, first hits, counts and best candidate -- with prebuilt coefficients and
-    ragged sizes as well (a last batch of 9 candidates; a skipped prefix of the index space)."""
+    """Obstacle tables are checked by k_pool (staged sections: plane stage with the certified solver skip, solve stage,
+    pair tasks in a warp pool); RQCD_POOL=0 selects k_check (lane-owns-trajectory, the kernel of the pairwise shape)
+    for them too. Both must give the oracle's verdicts, first hits, counts and best candidate -- with prebuilt
+    coefficients and ragged sizes as well (a last batch of 9 candidates; a skipped prefix of the index space)."""
     from rapidquadcoptercollisiondetection_b200.api import Context
     specs = W.static_obstacles(201, 20, 17)
     obs = abi.make_obstacles(specs)
@@ -156,6 +156,7 @@ def test_both_kernels_of_the_static_all_pairs_shape(oracle, monkeypatch):
         with Context(0) as c2:
             c2.set_obstacles(obs, m)
             r = c2.generate_check(bc, MIN_T, index_base=777)
+            assert c2.last_kernel_name().startswith("k_pool" if pool == "1" else "k_check")
             np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"])
             np.testing.assert_array_equal(r["verdict"], o["verdict"])
             np.testing.assert_array_equal(r["first_obstacle"], o["first_obstacle"])
