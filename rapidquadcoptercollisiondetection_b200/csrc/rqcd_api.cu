@@ -59,7 +59,7 @@ struct rqcd_ctx {
   int refill_min = 0;  // RQCD_REFILL_MIN override; 0 = chosen from the obstacle count
   int lockstep = -1;   // RQCD_LOCKSTEP override (0/1); -1 = chosen from the obstacle count
   int pool = 1;        // RQCD_POOL (0/1): k_pool (staged sections, certified solver skip) for obstacle tables
-  int th_solve = 24, th_plane = 20;  // RQCD_TH_SOLVE / RQCD_TH_PLANE: see CheckParams
+  int th_solve = 32, th_plane = 24;  // RQCD_TH_SOLVE / RQCD_TH_PLANE: see CheckParams
   long long stream_timeout = 1ll << 32;  // RQCD_STREAM_TIMEOUT_CYCLES (~2 s): a streamed chunk that never arrives fails the call
   const char* last_kernel = "";  // name of the check kernel of the most recent launch (rqcd_last_kernel_name)
   unsigned long long launches = 0;
@@ -576,6 +576,21 @@ int rqcd_set_obstacles(rqcd_ctx* ctx, const rqcd_obstacle* obstacles, int32_t m)
         F(OF_R + i) = R[i];
         F(OF_RI + i) = Ri[i];
       }
+    }
+    {
+      // ball around the centre that holds the obstacle, padded (far_from_obstacle in rqcd_device.cuh): the sphere's
+      // radius or the norm of the prism's half sides; none (+inf) unless the quaternion is a unit quaternion, i.e. the
+      // matrices above are rotations
+      double rb = o.radius;
+      if (o.type == RQCD_RECT_PRISM) {
+        const double h0 = o.side[0] / 2, h1 = o.side[1] / 2, h2 = o.side[2] / 2;
+        rb = std::sqrt(h0 * h0 + h1 * h1 + h2 * h2);
+        const double q2 = o.quat[0] * o.quat[0] + o.quat[1] * o.quat[1] + o.quat[2] * o.quat[2] + o.quat[3] * o.quat[3];
+        if (!(std::fabs(q2 - 1.0) <= 1e-12)) rb = std::numeric_limits<double>::infinity();
+      }
+      const double cn = std::fabs(o.center[0]) + std::fabs(o.center[1]) + std::fabs(o.center[2]) + 2 * rb;
+      F(OF_RBOUND) = rb * (1.0 + 2e-7) + 1e-10 * cn;  // 2e-7: a sphere's plane point is centre + r n with |n| = 1 +- 6e-8
+      if (o.moving) F(OF_RBOUND) = std::numeric_limits<double>::infinity();  // the cull is for static obstacles
     }
     if (o.moving) {
       flags |= OBS_MOVING;

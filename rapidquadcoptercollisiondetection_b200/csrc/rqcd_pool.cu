@@ -39,12 +39,84 @@ enum PoolRow {
   PR_PL = 24,   // plane (point, normal) of the task this LANE is running, between its PLANE and SOLVE stages
   kPoolRows = 30
 };
+constexpr int kQueueCap = 64;  // first sections waiting for their PLANE stage, per warp (owner << 16 | obstacle)
 enum LaneState { LS_IDLE = 0, LS_NEED_PLANE = 1, LS_NEED_SOLVE = 2 };
 enum PlaneStage { PS_CLEAR = 0, PS_COLLISION = 1, PS_INDETERM = 2, PS_SOLVE = 4 };
 
+// The compiler's own division and square root for a whole section when an operand of any lane left the range of the
+// regrouped sequences (see FastMath): rare, and kept out of line so that the hot loop stays inside the instruction cache.
+// (Arguments and results travel by value, the coefficients are re-read from the owner's rows: nothing of the caller's
+// register state needs an address.)
+struct PlainPlane {
+  V3 pp, pn;
+  bool in_m;
+};
+__device__ __noinline__ PlainPlane tangent_plane_plain(const double* rec, V3 Xm) {
+  TableObs obs;
+  obs.rec = rec;
+  PlainMath pm;
+  PlainPlane o;
+  tangent_plane(pm, obs, Xm, obs.center(), obs.radius(), obs.prism(), o.in_m, o.pp, o.pn);
+  return o;
+}
+struct PlainRoots {
+  double pc[5], r[4];
+  int n;
+};
+__device__ __noinline__ PlainRoots critical_times_plain(const double* crow, const double* motion, int row_stride, V3 pn) {
+  double c[18];
+#pragma unroll
+  for (int j = 0; j < 18; j++) c[j] = crow[(PR_C + j) * row_stride];
+  if (motion) {
+#pragma unroll
+    for (int j = 0; j < 18; j++) c[j] = c[j] - motion[j];
+  }
+  PlainMath pm;
+  PlainRoots o;
+  o.n = critical_times(pm, c, pn, o.pc, o.r[0], o.r[1], o.r[2], o.r[3]);
+  return o;
+}
+
+// One axis of RapidTrajectoryGenerator::Generate + GetTrajectory (gen_axis + axis_coeffs), out of line: the eight
+// goal-flag branches exist once instead of three times in the batch-build code, which shares the instruction cache
+// with the trip loop. Same arithmetic as load_trajectory (rqcd_kernel_util.cuh).
+struct AxisOut {
+  double k[6], cost;
+};
+__device__ __noinline__ AxisOut gen_axis_out(double p0, double v0, double a0, double pf, double vf, double af, unsigned goal3,
+                                             double Tf) {
+  const AxisParams q = gen_axis(p0, v0, a0, pf, vf, af, goal3 & 1u, (goal3 >> 1) & 1u, (goal3 >> 2) & 1u, Tf);
+  AxisOut o;
+  axis_coeffs(q, p0, v0, a0, o.k[0], o.k[1], o.k[2], o.k[3], o.k[4], o.k[5]);
+  o.cost = q.cost;
+  return o;
+}
+template <int MODE>
+RQCD_DEV void load_trajectory_compact(const CheckParams& p, long long i, double (&c)[18], double& t0, double& t1, double& cost) {
+  if (MODE == MODE_BC) {
+    const double* d = p.in;
+    const long long s = p.in_stride;
+    const double Tf = ld_in(d + 18 * s + i);
+    double total = 0.0;
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+      const AxisOut q = gen_axis_out(ld_in(d + (0 + ax) * s + i), ld_in(d + (3 + ax) * s + i), ld_in(d + (6 + ax) * s + i),
+                                     ld_in(d + (9 + ax) * s + i), ld_in(d + (12 + ax) * s + i), ld_in(d + (15 + ax) * s + i),
+                                     (p.goal_mask >> (3 * ax)) & 7u, Tf);
+#pragma unroll
+      for (int j = 0; j < 6; j++) c[3 * j + ax] = q.k[j];
+      total = (ax == 0) ? q.cost : total + q.cost;  // GetCost: cost[0] + cost[1] + cost[2] (.hpp:214-216)
+    }
+    cost = total;
+    t0 = 0.0;
+    t1 = Tf;
+  } else {
+    load_trajectory<MODE>(p, i, c, t0, t1, cost);
+  }
+}
+
 // The PLANE stage of one section (CollisionChecker.cpp:89-99 + the certified skip). All 32 lanes call it together.
-template <class Obs>
-RQCD_DEV int plane_stage(const double (&c)[18], const Obs& obs, V3 Xm, double ts, double tf, double amax, double minT,
+RQCD_DEV int plane_stage(const double (&c)[18], const TableObs& obs, V3 Xm, double ts, double tf, double amax, double minT,
                          bool active, V3& pp, V3& pn) {
   const V3 ctr = obs.center();
   const double rad = obs.radius();
@@ -54,8 +126,8 @@ RQCD_DEV int plane_stage(const double (&c)[18], const Obs& obs, V3 Xm, double ts
     FastMath f;
     tangent_plane(f, obs, Xm, ctr, rad, prism, in_m, pp, pn);
     if (!warp_all(f.ok | !active)) {
-      PlainMath pm;
-      tangent_plane(pm, obs, Xm, ctr, rad, prism, in_m, pp, pn);
+      const PlainPlane q = tangent_plane_plain(obs.rec, Xm);
+      in_m = q.in_m, pp = q.pp, pn = q.pn;
     }
   }
   const bool clear = bernstein_clear(c, pp, pn, ts, tf, amax);
@@ -80,7 +152,8 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
   long long* idx_row = reinterpret_cast<long long*>(rows + kPoolRows * T);            // [T]
   double* pool_pl = reinterpret_cast<double*>(idx_row + T);                           // [kWarps][6][kPoolCap]: planes
   int* pool_ok = reinterpret_cast<int*>(pool_pl + kWarps * 6 * kPoolCap);             // [kWarps][kPoolCap]: owner << 16 | k
-  unsigned* res = reinterpret_cast<unsigned*>(pool_ok + kWarps * kPoolCap);           // [T]: min (k << 2 | verdict)
+  int* queue = pool_ok + kWarps * kPoolCap;                                            // [kWarps][kQueueCap]: owner << 16 | k
+  unsigned* res = reinterpret_cast<unsigned*>(queue + kWarps * kQueueCap);             // [T]: min (k << 2 | verdict)
   unsigned* inbits = res + T;                                                         // [(mp + 31) / 32][T], static tables
   __shared__ __align__(8) uint64_t mbar;
 
@@ -103,6 +176,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
   double* my_row = rows + tid;
   double* wpool_pl = pool_pl + warp * 6 * kPoolCap;
   int* wpool_ok = pool_ok + warp * kPoolCap;
+  int* wqueue = queue + warp * kQueueCap;
   const unsigned lt_mask = (1u << lane) - 1u;
   double2 stack[kMaxDepth];  // the running task's parked low children {ts, lo_tf}
   unsigned long long avail = 0;
@@ -124,9 +198,10 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
     const long long idx = (long long)b + lane;
     const bool have = idx < p.n && !(p.skip && p.skip[idx] != 0);  // planner: dropped by an earlier stage
     double t0 = 0.0, t1 = 0.0, cost = 0.0;
-    V3 x0 = v3(0, 0, 0), x1 = v3(0, 0, 0);
+    V3 x0 = v3(0, 0, 0), x1 = v3(0, 0, 0), xm0 = v3(0, 0, 0);
+    double hull_r = __longlong_as_double(0x7ff0000000000000ll);  // bound of |X(t) - X(mid)| on the window; +inf: no cull
     if (have) {
-      load_trajectory<MODE>(p, idx, c, t0, t1, cost);
+      load_trajectory_compact<MODE>(p, idx, c, t0, t1, cost);
       if (MODE == MODE_BC) {
         if (p.cost) p.cost[idx] = cost;
         if (p.coeffs) {
@@ -138,7 +213,11 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
         x0 = traj_value(c, t0), x1 = traj_value(c, t1);
         const V3 xm = traj_value(c, (t0 + t1) / 2);  // the first section's midpoint (CollisionChecker.cpp:87), every obstacle
         my_row[(PR_XM + 0) * T] = xm.x, my_row[(PR_XM + 1) * T] = xm.y, my_row[(PR_XM + 2) * T] = xm.z;
-        my_row[PR_AMAX * T] = side_filter_bound(c, t0, t1);
+        const double amax0 = side_filter_bound(c, t0, t1);
+        my_row[PR_AMAX * T] = amax0;
+        xm0 = xm;
+        // a window shorter than minT makes every first section Indeterminable (:93-96): no cull then
+        if (!(t1 - t0 < p.min_t)) hull_r = traj_hull_radius(c, t0, t1, xm, amax0);
       }
       my_row[PR_T0 * T] = t0;
       my_row[PR_T1 * T] = t1;
@@ -164,7 +243,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
     __syncwarp();
 
     // ---- the batch. Lane state of a running task: owner, obstacle, interval, parked low children.
-    int st = LS_IDLE, owner = lane, kk = 0, sp = 0, pool_n = 0, k = 0;
+    int st = LS_IDLE, owner = lane, kk = 0, sp = 0, pool_n = 0, k = 0, q_n = 0;
     double ts = 0.0, tf = 0.0;
     unsigned n1 = 0, n2 = 0, n3 = 0;  // pairs this lane decided as Collision / Indeterminable / depth cap (all-pairs mode)
     for (;;) {
@@ -200,94 +279,117 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
       }
       const int n_plane = __popc(__ballot_sync(kFull, st == LS_NEED_PLANE));
       const int n_solve = __popc(__ballot_sync(kFull, st == LS_NEED_SOLVE));
-      const bool a_ok = k < m && pool_n <= kPoolCap - 32;
+      // ---- the cull pass feeds the queue of first sections: lane = own trajectory, obstacle k = broadcast loads. A pair
+      // whose end-point bit is set is a Collision without a section (:73-77); a pair whose obstacle is far from the whole
+      // trajectory (far_from_obstacle) is NoCollision without a plane; the others wait for an A trip.
+      while (k < m && q_n <= kQueueCap - 32) {
+        const double* rec = tab + (size_t)k * p.stride;
+        bool push = have && !(early && (res[tid] >> 2) < (unsigned)k);
+        if (!MOVING) {
+          const bool bit = (inbits[(k >> 5) * T + tid] >> (k & 31)) & 1u;
+          const bool far = far_from_obstacle(xm0, hull_r, v3(rec[OF_CX], rec[OF_CY], rec[OF_CZ]), rec[OF_RBOUND]);
+          if (push & bit) {
+            if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)1;
+            n1++;
+            atomicMin(&res[tid], ((unsigned)k << 2) | 1u);
+          } else if (push & far) {
+            if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)0;
+          }
+          push = push & !bit & !far;
+        }
+        const unsigned push_m = __ballot_sync(kFull, push);
+        if (push) wqueue[q_n + __popc(push_m & lt_mask)] = (lane << 16) | k;
+        q_n += __popc(push_m);
+        k++;
+      }
+      __syncwarp();
+      const bool a_ok = q_n > 0 && (q_n >= 32 || k >= m) && pool_n <= kPoolCap - 32;
       int trip;  // 0: A, 1: P, 2: S
       if (n_solve >= p.th_solve) trip = 2;
       else if (n_plane >= p.th_plane) trip = 1;
       else if (a_ok) trip = 0;
       else if (n_solve > 0 && n_solve >= n_plane) trip = 2;
       else if (n_plane > 0) trip = 1;
-      else break;  // table through, pool empty, no lane holds a task: the batch is done
+      else if (q_n > 0) trip = 0;
+      else break;  // table through, queue and pool empty, no lane holds a task: the batch is done
 
       int pv = -1;  // verdict of the task that ended in this trip, if any
-      if (trip == 0) {
-        // ---- A trip: the PLANE stage of the first section of (own trajectory, obstacle k)
-#pragma unroll
-        for (int j = 0; j < 18; j++) c[j] = my_row[(PR_C + j) * T];
-        const double* rec = tab + (size_t)k * p.stride;
-        bool active = have && !(early && (res[tid] >> 2) < (unsigned)k);
-        double a_ts = t0, a_tf = t1, amax;
-        V3 xm;
-        int pre = -1;  // decided before the section: 1 an end point is inside, 0 no common window
-        if (!MOVING) {
-          const bool bit = (inbits[(k >> 5) * T + tid] >> (k & 31)) & 1u;
-          if (active & bit) pre = 1;  // Collision without a section (:73-77)
-          xm = v3(my_row[(PR_XM + 0) * T], my_row[(PR_XM + 1) * T], my_row[(PR_XM + 2) * T]);
-          amax = my_row[PR_AMAX * T];
-        } else {
-          TableObs o;
-          o.rec = rec;
-          if (oflags[k] & OBS_MOVING) {  // warp-uniform
-            // Trajectory::operator- (Trajectory.hpp:121-128): coefficient-wise difference on the common window
-#pragma unroll
-            for (int j = 0; j < 18; j++) c[j] = c[j] - rec[OF_MOTION + j];
-            const double ms = rec[OF_MT0], me = rec[OF_MT1];
-            a_ts = (t0 < ms) ? ms : t0;
-            a_tf = (me < t1) ? me : t1;
-            if (active & !(a_ts <= a_tf)) pre = 0;  // no common time (the reference would assert, Trajectory.hpp:68)
-          }
-          const bool in_ends = ends_inside(o, traj_value(c, a_ts), traj_value(c, a_tf));
-          __syncwarp();
-          if (active & (pre < 0) & in_ends) pre = 1;
-          xm = traj_value(c, (a_ts + a_tf) / 2);
-          amax = side_filter_bound(c, a_ts, a_tf);
-        }
-        active = active & (pre < 0);
-        TableObs o;
-        o.rec = rec;
-        V3 pp, pn;
-        const int r = plane_stage(c, o, xm, a_ts, a_tf, amax, p.min_t, active, pp, pn);
-        const bool spawn = active & (r == PS_SOLVE);
-        const unsigned spawn_m = __ballot_sync(kFull, spawn);
-        if (spawn) {
-          const int slot = pool_n + __popc(spawn_m & lt_mask);
-          wpool_ok[slot] = (lane << 16) | k;
-          wpool_pl[0 * kPoolCap + slot] = pp.x, wpool_pl[1 * kPoolCap + slot] = pp.y, wpool_pl[2 * kPoolCap + slot] = pp.z;
-          wpool_pl[3 * kPoolCap + slot] = pn.x, wpool_pl[4 * kPoolCap + slot] = pn.y, wpool_pl[5 * kPoolCap + slot] = pn.z;
-        }
-        const int v = (pre >= 0) ? pre : (active ? (r & 3) : -1);  // PS_SOLVE & 3 == 0: NoCollision until the task says otherwise
-        if (v >= 0) {
-          if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)v;
-          if (v != 0) {
-            n1 += (v == 1), n2 += (v == 2);
-            atomicMin(&res[tid], ((unsigned)k << 2) | (unsigned)v);
-          }
-        }
-        pool_n += __popc(spawn_m);
-        __syncwarp();
-        k++;
-        continue;
+      // ---- every trip works on ONE section per lane: (trajectory of lane `o_lane`, obstacle `o_k`, [f_ts, f_tf]).
+      // A trip: the first section of (own trajectory, obstacle k); P and S trips: the lane's task.
+      const bool trip_a = trip == 0;
+      int a_lane = lane, a_k = 0;
+      bool a_have = false;
+      if (trip_a) {  // every lane takes a first section from the top of the queue
+        const int take_n = min(32, q_n);
+        a_have = lane < take_n;
+        const int e = wqueue[a_have ? q_n - 1 - lane : 0];
+        a_lane = e >> 16, a_k = e & 0xffff;
+        q_n -= take_n;
       }
-
-      // ---- P and S trips work on the lanes' tasks: the owner's coefficients (relative to a moving obstacle)
-      const double* orow = rows + (wbase + owner);
+      const int o_lane = trip_a ? a_lane : owner, o_k = trip_a ? a_k : kk;
+      const double* orow = rows + (wbase + o_lane);
+      const double* rec = tab + (size_t)o_k * p.stride;
 #pragma unroll
       for (int j = 0; j < 18; j++) c[j] = orow[(PR_C + j) * T];
-      const double* rec = tab + (size_t)kk * p.stride;
+      const double o_t0 = orow[PR_T0 * T], o_t1 = orow[PR_T1 * T];
+      double f_ts = trip_a ? o_t0 : ts, f_tf = trip_a ? o_t1 : tf;
+      bool active = trip_a ? (a_have && !(early && (res[wbase + a_lane] >> 2) < (unsigned)a_k))
+                           : (st == (trip == 1 ? LS_NEED_PLANE : LS_NEED_SOLVE));
+      int pre = -1;  // A trip, moving obstacle: decided before the section: 1 an end point is inside, 0 no common window
       if (MOVING) {
+        // Trajectory::operator- (Trajectory.hpp:121-128): coefficient-wise difference (zeros for a static obstacle of the
+        // table) on the common window
 #pragma unroll
-        for (int j = 0; j < 18; j++) c[j] = c[j] - rec[OF_MOTION + j];  // zeros for a static obstacle of the table
+        for (int j = 0; j < 18; j++) c[j] = c[j] - rec[OF_MOTION + j];
+        if (trip_a) {
+          if (oflags[o_k] & OBS_MOVING) {
+            const double ms = rec[OF_MT0], me = rec[OF_MT1];
+            f_ts = (o_t0 < ms) ? ms : o_t0;  // std::max(_startTime, rhs start)
+            f_tf = (me < o_t1) ? me : o_t1;  // std::min(_endTime, rhs end)
+            if (active & !(f_ts <= f_tf)) pre = 0;  // no common time (the reference would assert, Trajectory.hpp:68)
+          }
+          TableObs o;
+          o.rec = rec;
+          const bool in_ends = ends_inside(o, traj_value(c, f_ts), traj_value(c, f_tf));  // :73-77
+          __syncwarp();
+          if (active & (pre < 0) & in_ends) pre = 1;
+        }
       }
-      const double amax = MOVING ? side_filter_bound(c, ts, tf) : orow[PR_AMAX * T];
-      const double mid = (ts + tf) / 2;  // :87
-      if (trip == 1) {
-        // ---- P trip: the PLANE stage of a child section
-        const bool act = st == LS_NEED_PLANE;
+      active = active & (pre < 0);
+      const double amax = MOVING ? side_filter_bound(c, f_ts, f_tf) : orow[PR_AMAX * T];
+      const double mid = (f_ts + f_tf) / 2;  // :87
+
+      if (trip != 2) {
+        // ---- the PLANE stage. X(mid) of a static first section was evaluated when the batch was built.
+        V3 xm;
+        if (!MOVING && trip_a) xm = v3(orow[(PR_XM + 0) * T], orow[(PR_XM + 1) * T], orow[(PR_XM + 2) * T]);
+        else xm = traj_value(c, mid);
         TableObs o;
         o.rec = rec;
         V3 pp, pn;
-        const int r = plane_stage(c, o, traj_value(c, mid), ts, tf, amax, p.min_t, act, pp, pn);
-        if (act) {
+        const int r = plane_stage(c, o, xm, f_ts, f_tf, amax, p.min_t, active, pp, pn);
+        if (trip_a) {
+          // a first section: decided, or a task for the pool
+          const bool spawn = active & (r == PS_SOLVE);
+          const unsigned spawn_m = __ballot_sync(kFull, spawn);
+          if (spawn) {
+            const int slot = pool_n + __popc(spawn_m & lt_mask);
+            wpool_ok[slot] = (a_lane << 16) | a_k;
+            wpool_pl[0 * kPoolCap + slot] = pp.x, wpool_pl[1 * kPoolCap + slot] = pp.y, wpool_pl[2 * kPoolCap + slot] = pp.z;
+            wpool_pl[3 * kPoolCap + slot] = pn.x, wpool_pl[4 * kPoolCap + slot] = pn.y, wpool_pl[5 * kPoolCap + slot] = pn.z;
+          }
+          const int v = (pre >= 0) ? pre : (active ? (r & 3) : -1);  // PS_SOLVE & 3 == 0: NoCollision until the task says otherwise
+          if (v >= 0) {
+            if (p.verdict_matrix) p.verdict_matrix[idx_row[wbase + a_lane] * (long long)m + a_k] = (uint8_t)v;
+            if (v != 0) {
+              n1 += (v == 1), n2 += (v == 2);
+              atomicMin(&res[wbase + a_lane], ((unsigned)a_k << 2) | (unsigned)v);
+            }
+          }
+          pool_n += __popc(spawn_m);
+          __syncwarp();
+        } else if (active) {
+          // a child section of the lane's task
           if (r == PS_SOLVE) {
             my_row[(PR_PL + 0) * T] = pp.x, my_row[(PR_PL + 1) * T] = pp.y, my_row[(PR_PL + 2) * T] = pp.z;
             my_row[(PR_PL + 3) * T] = pn.x, my_row[(PR_PL + 4) * T] = pn.y, my_row[(PR_PL + 5) * T] = pn.z;
@@ -300,8 +402,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
           }
         }
       } else {
-        // ---- S trip: the SOLVE stage
-        const bool act = st == LS_NEED_SOLVE;
+        // ---- the SOLVE stage
         const V3 pp = v3(my_row[(PR_PL + 0) * T], my_row[(PR_PL + 1) * T], my_row[(PR_PL + 2) * T]);
         const V3 pn = v3(my_row[(PR_PL + 3) * T], my_row[(PR_PL + 4) * T], my_row[(PR_PL + 5) * T]);
         double pc[5], r0, r1, r2, r3;
@@ -309,14 +410,16 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
         {
           FastMath f;
           n = critical_times(f, c, pn, pc, r0, r1, r2, r3);
-          if (!warp_all(f.ok | !act)) {
-            PlainMath pm;
-            n = critical_times(pm, c, pn, pc, r0, r1, r2, r3);
+          if (!warp_all(f.ok | !active)) {
+            const PlainRoots q = critical_times_plain(orow, MOVING ? rec + OF_MOTION : nullptr, T, pn);
+            n = q.n, r0 = q.r[0], r1 = q.r[1], r2 = q.r[2], r3 = q.r[3];
+#pragma unroll
+            for (int j = 0; j < 5; j++) pc[j] = q.pc[j];
           }
         }
         Children ch;
-        section_children(c, ts, tf, mid, pp, pn, pc, n, r0, r1, r2, r3, amax, act, ch);
-        if (act) {
+        section_children(c, ts, tf, mid, pp, pn, pc, n, r0, r1, r2, r3, amax, active, ch);
+        if (active) {
           if (ch.has_hi | ch.has_lo) {
             if (ch.has_hi & ch.has_lo) {  // the parent's low tail call waits until the high subtree is clear
               if (sp < kMaxDepth) stack[sp++] = make_double2(ts, ch.lo_tf);
@@ -454,7 +557,7 @@ size_t pool_smem_bytes(int mp, int stride, int threads) {
   size_t u = (size_t)stride * mp * 8 + (size_t)mp * 4;  // table + flags (mp % 4 == 0 keeps 16-byte alignment)
   u += W * 8 * 8 + T * 16;                              // warp counters, best cost / index
   u += T * 8 * kPoolRows + T * 8;                       // trajectory rows, global indices
-  u += W * kPoolCap * (6 * 8 + 4);                      // task pools: planes, owner/obstacle words
+  u += W * kPoolCap * (6 * 8 + 4) + W * kQueueCap * 4;  // task pools (planes, owner/obstacle words), first-section queues
   u += T * 4 + (size_t)((mp + 31) / 32) * T * 4;        // verdict words, end-point bits
   return u;
 }
