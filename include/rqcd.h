@@ -20,7 +20,8 @@
  *  - there is no CPU fallback: without a CUDA device rqcd_create fails with
  *    RQCD_ERR_NO_DEVICE and nothing else can be called.
  *  - a context is bound to one GPU and one stream; use one context per host
- *    thread / per rank (one process per GPU under torchrun).
+ *    thread / per rank (one process per GPU under torchrun), or an rqcd_group
+ *    of contexts for several GPUs in one process.
  */
 #ifndef RQCD_H_
 #define RQCD_H_
@@ -113,9 +114,17 @@ enum {
 
 typedef struct rqcd_bc_soa {
   const double* data; /* RQCD_BC_ROWS rows */
-  int64_t stride;     /* doubles between rows, >= n */
+  int64_t stride;     /* doubles between rows, >= first + n */
   uint32_t goal_mask;
-  uint32_t reserved;
+  /* Rows that candidates share. The reference's Forest loop draws ONE initial state per batch of 100 candidates and
+   * varies only the goal position and the duration (test/ForestPerformanceEval.cpp:175-193); such a batch need not
+   * carry 19 doubles per candidate. Bit r set: row r holds one value per GROUP of group_size consecutive candidates
+   * (candidate i reads element i / group_size); with host pointers only those elements cross PCIe. 0 (default):
+   * every row is per candidate. */
+  uint32_t shared_rows;
+  int64_t group_size; /* >= 1 when shared_rows != 0 (a value >= first + n makes a shared row one constant) */
+  int64_t first;      /* the call's candidate 0 is element `first` of the per-candidate rows and belongs to group
+                         first / group_size: lets shards of one batch (rqcd_group_*, ranks) share one matrix. Default 0 */
 } rqcd_bc_soa;
 
 /* Pre-built quintics (CommonMath::Trajectory, Trajectory.hpp:44-69), structure-of-arrays:
@@ -282,12 +291,66 @@ int rqcd_plan_best(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const rqcd_p
 int rqcd_solve_cubic(rqcd_ctx* ctx, const double* coef, int64_t n, uint32_t flags, double* roots, int32_t* count);
 int rqcd_solve_quartic(rqcd_ctx* ctx, const double* coef, int64_t n, uint32_t flags, double* roots, int32_t* count);
 
-/* ---- multi-GPU plumbing ---------------------------------------------------
- * Shards are contiguous candidate ranges, one per rank; each rank holds the full obstacle set. The
- * only exchange is this merge of per-shard summaries (counts add; best = min cost, lowest index on
- * ties). It is pure host arithmetic so any transport (NCCL all-gather of the 96-byte records via
- * torch.distributed, MPI, ...) can carry the records. */
+/* ---- multi-GPU ---------------------------------------------------------------
+ * Candidates are sharded by index into contiguous ranges, one per GPU; each GPU holds the full obstacle set. The only
+ * exchange is the merge of the per-shard summaries (counts add; best = min cost, lowest index on ties), 88 bytes per
+ * shard -- the reduction the drivers' loops do on the host (ForestPerformanceEval.cpp:216-230 counts verdicts; a planner
+ * keeps the cheapest collision-free candidate). Two ways to run it, both inside this library, neither with a host round
+ * trip between the check kernel and the merged record:
+ *
+ * (1) one process, several GPUs (a C++ host): rqcd_group_*. Each device's summary is stored by a one-thread kernel
+ *     into its slot of a table in the FIRST device's memory through the NVLink peer mapping (mapped host memory when
+ *     the devices cannot reach each other), and a merge kernel there applies the rule.
+ * (2) one process per GPU (torchrun, MPI): rqcd_comm_* + rqcd_exchange_summaries. The context owns an NCCL
+ *     communicator; the exchange is an ncclAllGather of the records on the context's stream followed by the same
+ *     merge kernel on every rank. libnccl.so.2 is loaded at rqcd_comm_init time (dlopen; RQCD_NCCL_LIB overrides the
+ *     name), so hosts that never call it do not need NCCL.
+ *
+ * rqcd_merge_summaries is the same rule as pure host arithmetic, for hosts that carry the records themselves. */
 int rqcd_merge_summaries(const rqcd_summary* shards, int32_t n_shards, rqcd_summary* merged);
+
+/* [lo, hi) of shard k of n candidates over n_shards: [k*n/n_shards, (k+1)*n/n_shards). */
+void rqcd_shard_range(int64_t n, int32_t k, int32_t n_shards, int64_t* lo, int64_t* hi);
+
+/* (1) device group. devices may name a device more than once (two shards on one GPU; used by the tests). */
+typedef struct rqcd_group rqcd_group;
+int rqcd_group_create(rqcd_group** group, const int32_t* devices, int32_t n_devices);
+void rqcd_group_destroy(rqcd_group* group);
+int32_t rqcd_group_size(const rqcd_group* group);
+rqcd_ctx* rqcd_group_ctx(rqcd_group* group, int32_t k); /* shard k's context (streams, tuning, errors) */
+const char* rqcd_group_last_error(const rqcd_group* group);
+int rqcd_group_peer_slots(const rqcd_group* group);     /* 1: summary slots are peer-mapped device memory, 0: mapped host memory */
+/* rqcd_set_obstacles on every device of the group. */
+int rqcd_group_set_obstacles(rqcd_group* group, const rqcd_obstacle* obstacles, int32_t m);
+/* rqcd_generate_check over the whole group with HOST buffers: shard k takes candidates rqcd_shard_range(n, k, size)
+ * of `in` and writes the same range of every array in `out`; each shard runs rqcd_generate_check's streaming host
+ * pipeline on its own device from its own host thread. out->summary (HOST, may be NULL) receives the merged record.
+ * RQCD_F_DEVICE_PTRS is not allowed here. */
+int rqcd_group_generate_check(rqcd_group* group, const rqcd_bc_soa* in, int64_t n, double min_time_section,
+                              uint32_t flags, rqcd_out* out);
+/* The same with shards already RESIDENT on their devices: in[k], n[k], out[k] (device pointers on device k, out may be
+ * NULL, out[k].summary ignored) describe shard k; index_base of shard k is index_base + n[0] + .. + n[k-1]. The call
+ * only enqueues (check, publish, merge); merged (HOST, may be NULL) makes it wait for and return the merged record,
+ * otherwise rqcd_group_read_summary does. */
+int rqcd_group_generate_check_resident(rqcd_group* group, const rqcd_bc_soa* in, const int64_t* n,
+                                       double min_time_section, uint32_t flags, int64_t index_base,
+                                       const rqcd_out* out, rqcd_summary* merged);
+int rqcd_group_read_summary(rqcd_group* group, rqcd_summary* merged);
+
+/* (2) one rank per process. The 128-byte id comes from rqcd_comm_unique_id on one rank and reaches the others over
+ * the host's own transport (torch.distributed broadcast, MPI_Bcast, a file). */
+#define RQCD_COMM_ID_BYTES 128
+int rqcd_comm_unique_id(void* id);
+int rqcd_comm_init(rqcd_ctx* ctx, const void* id, int32_t rank, int32_t world);
+int rqcd_comm_finalize(rqcd_ctx* ctx);
+int32_t rqcd_comm_world(const rqcd_ctx* ctx);  /* 1 without a communicator */
+/* Enqueues, on the context's stream, the all-gather of the most recent check launch's summary and its merge; every
+ * rank ends up with the same merged record in device memory. d_record (DEVICE pointer, may be NULL) receives a copy,
+ * e.g. a slot of a per-step ring that is read once after many steps. Without a communicator (world 1) the merge is of
+ * the one local record. No host synchronisation. */
+int rqcd_exchange_summaries(rqcd_ctx* ctx, rqcd_summary* d_record);
+/* Waits for the stream and returns the merged record of the last rqcd_exchange_summaries. */
+int rqcd_read_merged_summary(rqcd_ctx* ctx, rqcd_summary* merged);
 
 /* ---- synthetic inputs -------------------------------------------------------
  * Counter-based generator shared by host oracle and device (splitmix64 of (seed, global index, row)),

@@ -24,6 +24,7 @@ GOAL_ALL = 0x1FF
 F_DEVICE_PTRS = 0x1
 F_EARLY_EXIT = 0x2
 MAX_DEPTH = 40
+COMM_ID_BYTES = 128
 
 
 def goal_pos(axis: int) -> int:
@@ -53,7 +54,9 @@ class Obstacle(C.Structure):
 
 
 class BcSoa(C.Structure):
-    _fields_ = [("data", C.c_void_p), ("stride", C.c_int64), ("goal_mask", C.c_uint32), ("reserved", C.c_uint32)]
+    # shared_rows / group_size / first: rows shared by groups of consecutive candidates, see rqcd.h (0, 0, 0 = none)
+    _fields_ = [("data", C.c_void_p), ("stride", C.c_int64), ("goal_mask", C.c_uint32), ("shared_rows", C.c_uint32),
+                ("group_size", C.c_int64), ("first", C.c_int64)]
 
 
 class CoeffSoa(C.Structure):
@@ -139,6 +142,24 @@ SYMBOLS = {
     "rqcd_solve_cubic": (C.c_int, [_VP, _VP, C.c_int64, C.c_uint32, _VP, _VP]),
     "rqcd_solve_quartic": (C.c_int, [_VP, _VP, C.c_int64, C.c_uint32, _VP, _VP]),
     "rqcd_merge_summaries": (C.c_int, [C.POINTER(Summary), C.c_int32, C.POINTER(Summary)]),
+    "rqcd_shard_range": (None, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "rqcd_group_create": (C.c_int, [C.POINTER(_VP), C.POINTER(C.c_int32), C.c_int32]),
+    "rqcd_group_destroy": (None, [_VP]),
+    "rqcd_group_size": (C.c_int32, [_VP]),
+    "rqcd_group_ctx": (_VP, [_VP, C.c_int32]),
+    "rqcd_group_last_error": (C.c_char_p, [_VP]),
+    "rqcd_group_peer_slots": (C.c_int, [_VP]),
+    "rqcd_group_set_obstacles": (C.c_int, [_VP, C.POINTER(Obstacle), C.c_int32]),
+    "rqcd_group_generate_check": (C.c_int, [_VP, C.POINTER(BcSoa), C.c_int64, C.c_double, C.c_uint32, C.POINTER(Out)]),
+    "rqcd_group_generate_check_resident": (C.c_int, [_VP, C.POINTER(BcSoa), C.POINTER(C.c_int64), C.c_double, C.c_uint32,
+                                                     C.c_int64, C.POINTER(Out), C.POINTER(Summary)]),
+    "rqcd_group_read_summary": (C.c_int, [_VP, C.POINTER(Summary)]),
+    "rqcd_comm_unique_id": (C.c_int, [_VP]),
+    "rqcd_comm_init": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32]),
+    "rqcd_comm_finalize": (C.c_int, [_VP]),
+    "rqcd_comm_world": (C.c_int32, [_VP]),
+    "rqcd_exchange_summaries": (C.c_int, [_VP, _VP]),
+    "rqcd_read_merged_summary": (C.c_int, [_VP, C.POINTER(Summary)]),
     "rqcd_synth_bc": (C.c_int, [_VP, C.c_uint64, C.c_int64, C.c_int64, _VP, C.c_int64]),
     "rqcd_measure_fp64_peak": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

@@ -29,21 +29,45 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def bc_soa(bc, n=None, goal_mask=abi.GOAL_ALL, shared_rows=0, group_size=0, first=0, stride=None):
+    """rqcd_bc_soa over a (19, stride) numpy array or a raw pointer. shared_rows: iterable of row numbers or a bit mask."""
+    if not isinstance(shared_rows, int):
+        mask = 0
+        for r in shared_rows:
+            mask |= 1 << int(r)
+        shared_rows = mask
+    if stride is None:
+        stride = bc.shape[1]
+    return abi.BcSoa(_ptr(bc), stride, goal_mask, shared_rows, group_size, first)
+
+
+def shared_row_mask(rows) -> int:
+    m = 0
+    for r in rows:
+        m |= 1 << int(r)
+    return m
+
+
 class Context:
     """rqcd_ctx: one GPU, one stream."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _handle=None):
         self.lib = abi.load()
-        h = C.c_void_p()
-        st = self.lib.rqcd_create(C.byref(h), device)
-        if st != abi.OK:
-            raise RqcdError(st, self.lib.rqcd_strerror(st).decode())
+        self._owned = _handle is None
+        if _handle is None:
+            h = C.c_void_p()
+            st = self.lib.rqcd_create(C.byref(h), device)
+            if st != abi.OK:
+                raise RqcdError(st, self.lib.rqcd_strerror(st).decode())
+        else:
+            h = C.c_void_p(_handle)  # a context owned by an rqcd_group
         self.h = h
         self.device = device
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.rqcd_destroy(self.h)
+            if self._owned:
+                self.lib.rqcd_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -101,13 +125,14 @@ class Context:
         return int(self.lib.rqcd_num_obstacles(self.h))
 
     # ---- host-mode calls (numpy in / numpy out) ----
-    def generate(self, bc, goal_mask=abi.GOAL_ALL):
+    def generate(self, bc, goal_mask=abi.GOAL_ALL, n=None, shared_rows=0, group_size=0, first=0):
         bc = np.ascontiguousarray(bc, dtype=np.float64)
-        n = bc.shape[1]
+        if n is None:
+            n = bc.shape[1] - first
         cost = np.empty(n)
         coeffs = np.empty((abi.COEFF_ROWS, n))
         out = abi.Out(cost=_ptr(cost), coeffs=_ptr(coeffs), coeff_stride=n)
-        inp = abi.BcSoa(_ptr(bc), n, goal_mask, 0)
+        inp = bc_soa(bc, n, goal_mask, shared_rows, group_size, first)
         self._chk(self.lib.rqcd_generate(self.h, C.byref(inp), n, 0, C.byref(out)))
         return {"cost": cost, "coeffs": coeffs}
 
@@ -126,12 +151,16 @@ class Context:
                       coeffs=_ptr(res.get("coeffs")), coeff_stride=n, summary=C.pointer(summ))
         return res, out, summ
 
-    def generate_check(self, bc, min_t, goal_mask=abi.GOAL_ALL, flags=0, index_base=0, matrix=True):
+    def generate_check(self, bc, min_t, goal_mask=abi.GOAL_ALL, flags=0, index_base=0, matrix=True, n=None, shared_rows=0,
+                       group_size=0, first=0):
+        """bc: (19, stride) array. With shared_rows (bit mask or row numbers) pass n explicitly: the shared rows hold one
+        value per group of group_size candidates, the per-candidate rows n values from element `first`."""
         bc = np.ascontiguousarray(bc, dtype=np.float64)
-        n = bc.shape[1]
+        if n is None:
+            n = bc.shape[1] - first
         m = self.num_obstacles()
         res, out, summ = self._host_out(n, m, matrix and not (flags & abi.F_EARLY_EXIT), True)
-        inp = abi.BcSoa(_ptr(bc), n, goal_mask, 0)
+        inp = bc_soa(bc, n, goal_mask, shared_rows, group_size, first)
         st = self._chk(self.lib.rqcd_generate_check(self.h, C.byref(inp), n, min_t, flags, index_base, C.byref(out)),
                        allow=(abi.ERR_DEPTH_CAP,))
         res["summary"] = summ.as_dict()
@@ -192,14 +221,15 @@ class Context:
         return verdict, matrix
 
     def input_feasibility(self, bc, goal_mask=abi.GOAL_ALL, gravity=(0.0, 0.0, -9.81), fmin=5.0, fmax=30.0, wmax=20.0,
-                          min_t=0.002, group=None):
+                          min_t=0.002, group=None, n=None, shared_rows=0, group_size=0, first=0):
         bc = np.ascontiguousarray(bc, dtype=np.float64)
-        n = bc.shape[1]
+        if n is None:
+            n = bc.shape[1] - first
         g = np.asarray(gravity, dtype=np.float64)
         if group is not None:
             group = np.ascontiguousarray(group, dtype=np.int64)
         res = np.full(n, 255, dtype=np.uint8)
-        inp = abi.BcSoa(_ptr(bc), n, goal_mask, 0)
+        inp = bc_soa(bc, n, goal_mask, shared_rows, group_size, first)
         self._chk(self.lib.rqcd_check_input_feasibility(self.h, C.byref(inp), n, _ptr(g), fmin, fmax, wmax, min_t, _ptr(group), 0,
                                                   _ptr(res)))
         return res
@@ -249,12 +279,12 @@ class Context:
 
     def generate_check_dev(self, d_bc: int, stride: int, n: int, min_t: float, goal_mask=abi.GOAL_ALL, flags=0,
                            index_base=0, d_verdict=0, d_first=0, d_matrix=0, d_cost=0, d_coeffs=0, coeff_stride=0,
-                           want_summary=False):
+                           want_summary=False, shared_rows=0, group_size=0, first=0):
         summ = abi.Summary()
         out = abi.Out(verdict=d_verdict or None, first_obstacle=d_first or None, verdict_matrix=d_matrix or None,
                       cost=d_cost or None, coeffs=d_coeffs or None, coeff_stride=coeff_stride,
                       summary=C.pointer(summ) if want_summary else None)
-        inp = abi.BcSoa(C.c_void_p(d_bc), stride, goal_mask, 0)
+        inp = abi.BcSoa(C.c_void_p(d_bc), stride, goal_mask, shared_rows, group_size, first)
         st = self._chk(self.lib.rqcd_generate_check(self.h, C.byref(inp), n, min_t, flags | abi.F_DEVICE_PTRS,
                                                     index_base, C.byref(out)), allow=(abi.ERR_DEPTH_CAP,))
         return summ.as_dict() if want_summary else st
@@ -271,10 +301,138 @@ class Context:
                        allow=(abi.ERR_DEPTH_CAP,))
         return summ.as_dict() if want_summary else st
 
+    # ---- one rank per process: the in-library NCCL exchange ----
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(bytes(unique_id), abi.COMM_ID_BYTES)
+        self._chk(self.lib.rqcd_comm_init(self.h, buf, rank, world))
+
+    def comm_finalize(self):
+        self._chk(self.lib.rqcd_comm_finalize(self.h))
+
+    def comm_world(self) -> int:
+        return int(self.lib.rqcd_comm_world(self.h))
+
+    def exchange_summaries(self, d_record: int = 0):
+        """Enqueue all-gather + merge of the last launch's summary on the context's stream (no host sync)."""
+        self._chk(self.lib.rqcd_exchange_summaries(self.h, C.c_void_p(d_record) if d_record else None))
+
+    def read_merged_summary(self) -> dict:
+        s = abi.Summary()
+        self._chk(self.lib.rqcd_read_merged_summary(self.h, C.byref(s)), allow=(abi.ERR_DEPTH_CAP,))
+        return s.as_dict()
+
     def measure_fp64_peak(self, millis=200):
         a, b = C.c_double(), C.c_double()
         self._chk(self.lib.rqcd_measure_fp64_peak(self.h, millis, C.byref(a), C.byref(b)))
         return {"dfma_flops": a.value, "dmul_dadd_flops": b.value}
+
+
+def comm_unique_id() -> bytes:
+    """rqcd_comm_unique_id: the 128-byte NCCL id one rank creates and the host's transport hands to the others."""
+    lib = abi.load()
+    buf = C.create_string_buffer(abi.COMM_ID_BYTES)
+    st = lib.rqcd_comm_unique_id(buf)
+    if st != abi.OK:
+        raise RqcdError(st, lib.rqcd_strerror(st).decode())
+    return buf.raw
+
+
+class Group:
+    """rqcd_group: several GPUs in one process; candidates sharded by index, summaries merged on the first device."""
+
+    def __init__(self, devices):
+        self.lib = abi.load()
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        st = self.lib.rqcd_group_create(C.byref(h), devs, len(devices))
+        if st != abi.OK:
+            raise RqcdError(st, self.lib.rqcd_strerror(st).decode())
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rqcd_group_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, st, allow=()):
+        if st != abi.OK and st not in allow:
+            raise RqcdError(st, self.lib.rqcd_strerror(st).decode(), self.lib.rqcd_group_last_error(self.h).decode())
+        return st
+
+    def size(self) -> int:
+        return int(self.lib.rqcd_group_size(self.h))
+
+    def peer_slots(self) -> bool:
+        return bool(self.lib.rqcd_group_peer_slots(self.h))
+
+    def ctx(self, k: int) -> Context:
+        return Context(self.devices[k], _handle=self.lib.rqcd_group_ctx(self.h, k))
+
+    def launch_count(self) -> int:
+        return sum(int(self.lib.rqcd_launch_count(self.lib.rqcd_group_ctx(self.h, k))) for k in range(self.size()))
+
+    def set_obstacles(self, obstacles, m=None):
+        if m is None:
+            m = len(obstacles)
+        self._chk(self.lib.rqcd_group_set_obstacles(self.h, obstacles, m))
+        self.m = m
+
+    def generate_check(self, bc, min_t, goal_mask=abi.GOAL_ALL, flags=0, matrix=True, n=None, shared_rows=0, group_size=0,
+                       first=0):
+        """Host buffers in, host buffers out, the whole group (rqcd_group_generate_check)."""
+        bc = np.ascontiguousarray(bc, dtype=np.float64)
+        if n is None:
+            n = bc.shape[1] - first
+        m = self.m
+        res = {"verdict": np.full(n, 255, dtype=np.uint8), "first_obstacle": np.full(n, -2, dtype=np.int32),
+               "cost": np.empty(n), "coeffs": np.empty((abi.COEFF_ROWS, n))}
+        if matrix and not (flags & abi.F_EARLY_EXIT):
+            res["verdict_matrix"] = np.full((n, max(m, 1)), 255, dtype=np.uint8)
+        summ = abi.Summary()
+        out = abi.Out(verdict=_ptr(res["verdict"]), first_obstacle=_ptr(res["first_obstacle"]),
+                      verdict_matrix=_ptr(res.get("verdict_matrix")), cost=_ptr(res["cost"]), coeffs=_ptr(res["coeffs"]),
+                      coeff_stride=n, summary=C.pointer(summ))
+        inp = bc_soa(bc, n, goal_mask, shared_rows, group_size, first)
+        st = self._chk(self.lib.rqcd_group_generate_check(self.h, C.byref(inp), n, min_t, flags, C.byref(out)),
+                       allow=(abi.ERR_DEPTH_CAP,))
+        res["summary"] = summ.as_dict()
+        res["status"] = st
+        return res
+
+    def generate_check_resident(self, d_bc, strides, ns, min_t, goal_mask=abi.GOAL_ALL, flags=0, index_base=0,
+                                d_verdict=None, d_first=None, d_cost=None, want_summary=True):
+        """Shards resident on their devices: per-shard lists of device pointers / strides / counts."""
+        G = self.size()
+        ins = (abi.BcSoa * G)()
+        outs = (abi.Out * G)()
+        cnt = (C.c_int64 * G)(*ns)
+        for k in range(G):
+            ins[k] = abi.BcSoa(C.c_void_p(d_bc[k]), strides[k], goal_mask, 0, 0, 0)
+            outs[k] = abi.Out(verdict=d_verdict[k] if d_verdict else None, first_obstacle=d_first[k] if d_first else None,
+                              cost=d_cost[k] if d_cost else None)
+        summ = abi.Summary()
+        st = self._chk(self.lib.rqcd_group_generate_check_resident(self.h, ins, cnt, min_t, flags, index_base, outs,
+                                                                    C.byref(summ) if want_summary else None),
+                       allow=(abi.ERR_DEPTH_CAP,))
+        return summ.as_dict() if want_summary else st
+
+    def read_summary(self) -> dict:
+        s = abi.Summary()
+        self._chk(self.lib.rqcd_group_read_summary(self.h, C.byref(s)), allow=(abi.ERR_DEPTH_CAP,))
+        return s.as_dict()
 
 
 def merge_summaries(summaries) -> dict:

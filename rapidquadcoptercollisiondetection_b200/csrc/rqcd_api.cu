@@ -15,6 +15,7 @@
 
 #include "../../include/rqcd.h"
 #include "rqcd_device.cuh"
+#include "rqcd_host.cuh"
 #include "rqcd_kernels.cuh"
 
 using namespace rqcd;
@@ -23,73 +24,6 @@ static_assert(RQCD_MAX_DEPTH == kMaxDepth, "RQCD_MAX_DEPTH and the device stack 
 static_assert(sizeof(DevSummary) == sizeof(rqcd_summary), "DevSummary mirrors rqcd_summary");
 
 namespace {
-
-constexpr size_t kMaxSmem = 227 * 1024;
-constexpr int kMaxChunks = 64;
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-};
-
-}  // namespace
-
-struct rqcd_ctx {
-  int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaStream_t h2d_stream = nullptr;                         // host-pointer calls: input streams in beside the kernel
-  cudaEvent_t ev_in = nullptr, ev_start = nullptr;
-  long long chunk_override = 0;                              // RQCD_HOST_CHUNK: candidates per chunk (0 = automatic)
-  cudaDeviceProp prop;
-  // obstacle set
-  int m = 0, mp = 0, stride = OF_STATIC_FIELDS;  // record stride in doubles (odd)
-  bool any_moving = false;
-  DevBuf obs_blob;
-  // launch scratch
-  unsigned long long* d_counter = nullptr;
-  BlockPartial* d_partials = nullptr;
-  int partial_cap = 0;
-  DevSummary* d_summary = nullptr;
-  DevSummary* h_summary = nullptr;  // pinned
-  unsigned long long* d_stream = nullptr;  // [0] progress, [1] error flag (streaming host-pointer calls)
-  unsigned long long* h_stream = nullptr;  // pinned: [0..kMaxChunks) cumulative counts, [kMaxChunks] error read-back
-  bool summary_valid = false;
-  // staging for host-pointer calls
-  DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group;
-  int refill_min = 0;  // RQCD_REFILL_MIN override; 0 = chosen from the obstacle count
-  int lockstep = -1;   // RQCD_LOCKSTEP override (0/1); -1 = chosen from the obstacle count
-  int pool = 1;        // RQCD_POOL (0/1): k_pool (staged sections, certified solver skip) for obstacle tables
-  int th_solve = 32, th_plane = 24;  // RQCD_TH_SOLVE / RQCD_TH_PLANE: see CheckParams
-  long long stream_timeout = 1ll << 32;  // RQCD_STREAM_TIMEOUT_CYCLES (~2 s): a streamed chunk that never arrives fails the call
-  const char* last_kernel = "";  // name of the check kernel of the most recent launch (rqcd_last_kernel_name)
-  unsigned long long launches = 0;
-  char last_error[512] = {0};
-};
-
-namespace {
-
-int fail_cuda(rqcd_ctx* c, cudaError_t e, const char* what) {
-  snprintf(c->last_error, sizeof c->last_error, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
-  return RQCD_ERR_CUDA;
-}
-
-#define RQCD_CU(call)                                        \
-  do {                                                       \
-    cudaError_t e_ = (call);                                 \
-    if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call); \
-  } while (0)
-
-struct DeviceGuard {  // the context's device is current for the duration of a call
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-    else prev = -1;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
 
 cudaError_t ensure(DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return cudaSuccess;
@@ -164,18 +98,68 @@ struct RowBlock {  // host rows still to be copied: row r goes to dst + r*n (dev
   const double* src;
   long long src_stride;
   int rows;
+  long long count;  // < 0: one element per candidate (copied chunk by chunk); else elements per row, copied before chunk 0
 };
 
-struct CheckCall {
+constexpr int kMaxBlocks = RQCD_BC_ROWS + 4;
+
+struct BlockList {
+  RowBlock blocks[kMaxBlocks];
+  int nblocks = 0;
+  void add(void* dst, const double* src, long long src_stride, int rows, long long count = -1) {
+    blocks[nblocks++] = RowBlock{(double*)dst, src, src_stride, rows, count};
+  }
+};
+
+struct CheckCall : BlockList {
   int mode = MODE_BC;
   bool pairwise = false;
   CheckParams p = {};
-  RowBlock blocks[5];
-  int nblocks = 0;
-  void add(void* dst, const double* src, long long src_stride, int rows) {
-    blocks[nblocks++] = RowBlock{(double*)dst, src, src_stride, rows};
-  }
 };
+
+// ---- rqcd_bc_soa ------------------------------------------------------------------------------------------------------
+bool bad_bc(const rqcd_bc_soa* in, long long n) {
+  if (!in || n < 0 || in->first < 0) return true;
+  if (n > 0 && !in->data) return true;
+  if ((in->shared_rows >> RQCD_BC_ROWS) != 0u) return true;
+  if (in->shared_rows != 0u && in->group_size < 1) return true;
+  return in->stride < in->first + n;
+}
+
+// device pointers: the kernel reads the caller's matrix in place
+void bind_bc(CheckParams& p, const rqcd_bc_soa* in) {
+  p.in = in->data;
+  p.in_stride = in->stride;
+  p.goal_mask = in->goal_mask;
+  p.shared_rows = in->shared_rows;
+  p.in_first = in->first;
+  p.grp_first = in->first;
+  p.group_size = in->shared_rows ? in->group_size : 1;
+}
+
+// host pointers: the rows of candidates [first, first + n) go to a staging matrix of RQCD_BC_ROWS x n doubles; of a
+// shared row only the groups those candidates belong to cross PCIe. Runs of rows of one kind are one pitched copy.
+void stage_bc(CheckParams& p, BlockList& bl, const rqcd_bc_soa* in, long long n, void* staging) {
+  double* dst = (double*)staging;
+  const long long G = in->shared_rows ? in->group_size : 1;
+  const long long g0 = in->first / G;
+  const long long ng = n > 0 ? (in->first + n - 1) / G - g0 + 1 : 0;
+  for (int r = 0; r < RQCD_BC_ROWS;) {
+    const unsigned kind = (in->shared_rows >> r) & 1u;
+    int e = r + 1;
+    while (e < RQCD_BC_ROWS && ((in->shared_rows >> e) & 1u) == kind) e++;
+    if (kind) bl.add(dst + (long long)r * n, in->data + (long long)r * in->stride + g0, in->stride, e - r, ng);
+    else bl.add(dst + (long long)r * n, in->data + (long long)r * in->stride + in->first, in->stride, e - r);
+    r = e;
+  }
+  p.in = dst;
+  p.in_stride = n;
+  p.goal_mask = in->goal_mask;
+  p.shared_rows = in->shared_rows;
+  p.in_first = 0;
+  p.grp_first = in->first - g0 * G;
+  p.group_size = G;
+}
 
 int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   const bool moving = !cc.pairwise && ctx->any_moving;
@@ -251,13 +235,22 @@ int fetch_summary(rqcd_ctx* ctx, rqcd_summary* out) {
 bool bad_min_t(double t) { return !(t > 0) || !std::isfinite(t); }
 
 // Host <-> device staging of row matrices (row r at base + r*stride, n doubles each).
-cudaError_t rows_h2d(void* dst, const double* src, long long stride, long long n, int rows, cudaStream_t s) {
-  if (n == 0) return cudaSuccess;
-  return cudaMemcpy2DAsync(dst, (size_t)n * 8, src, (size_t)stride * 8, (size_t)n * 8, rows, cudaMemcpyHostToDevice, s);
-}
 cudaError_t rows_d2h(double* dst, long long stride, const void* src, long long n, int rows, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   return cudaMemcpy2DAsync(dst, (size_t)stride * 8, src, (size_t)n * 8, (size_t)n * 8, rows, cudaMemcpyDeviceToHost, s);
+}
+
+// every block in full (the calls that do not stream their input beside the kernel)
+cudaError_t copy_blocks(const BlockList& bl, long long n, cudaStream_t s) {
+  for (int b = 0; b < bl.nblocks; b++) {
+    const RowBlock& rb = bl.blocks[b];
+    const long long w = rb.count < 0 ? n : rb.count;
+    if (w == 0) continue;
+    cudaError_t e = cudaMemcpy2DAsync(rb.dst, (size_t)n * 8, rb.src, (size_t)rb.src_stride * 8, (size_t)w * 8, rb.rows,
+                                      cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 struct OutStage {  // device-side output pointers + what must be copied back
@@ -338,6 +331,7 @@ int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long lo
     const long long w = c1 - c0;
     for (int b = 0; b < cc.nblocks && w > 0; b++) {
       const RowBlock& rb = cc.blocks[b];
+      if (rb.count >= 0) continue;  // shared rows went ahead of the first chunk
       cudaError_t e = cudaMemcpy2DAsync(rb.dst + c0, (size_t)n * 8, rb.src + c0, (size_t)rb.src_stride * 8,
                                         (size_t)w * 8, rb.rows, cudaMemcpyHostToDevice, hs);
       if (e != cudaSuccess) return e;
@@ -349,6 +343,12 @@ int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long lo
   // ordered on the copy stream, the compute stream only waits for the first chunk. After its launch the kernel never
   // depends on further host progress, so a blocking or serialised launch (CUDA_LAUNCH_BLOCKING, a profiler's kernel
   // replay, a descheduled host thread) cannot turn a valid call into a time-out.
+  for (int b = 0; b < cc.nblocks; b++) {
+    const RowBlock& rb = cc.blocks[b];
+    if (rb.count > 0)
+      RQCD_CU(cudaMemcpy2DAsync(rb.dst, (size_t)n * 8, rb.src, (size_t)rb.src_stride * 8, (size_t)rb.count * 8, rb.rows,
+                                cudaMemcpyHostToDevice, hs));
+  }
   const long long first_end = chunk < n ? chunk : n;
   RQCD_CU(copy_chunk(0, 0, first_end));
   RQCD_CU(cudaEventRecord(ctx->ev_in, hs));
@@ -423,6 +423,7 @@ int rqcd_create(rqcd_ctx** out, int device) {
   rqcd_ctx* ctx = new (std::nothrow) rqcd_ctx();
   if (!ctx) return RQCD_ERR_NOMEM;
   ctx->device = device;
+  ctx->stride = OF_STATIC_FIELDS;
   if (cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess || ctx->prop.major < 10) {
     cudaGetLastError();
     delete ctx;
@@ -467,6 +468,8 @@ void rqcd_destroy(rqcd_ctx* ctx) {
   if (!ctx) return;
   DeviceGuard g(ctx->device);
   if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  rqcd_comm_finalize(ctx);
+  if (ctx->d_merged) cudaFree(ctx->d_merged);
   release(ctx->obs_blob);
   DevBuf* bufs[] = {&ctx->s_in,     &ctx->s_aux,   &ctx->s_verdict, &ctx->s_first,  &ctx->s_matrix, &ctx->s_cost,
                     &ctx->s_coeffs, &ctx->s_roots, &ctx->s_count,   &ctx->s_planes, &ctx->s_peaks,  &ctx->s_group};
@@ -614,17 +617,22 @@ int rqcd_set_obstacles(rqcd_ctx* ctx, const rqcd_obstacle* obstacles, int32_t m)
 int32_t rqcd_num_obstacles(const rqcd_ctx* ctx) { return ctx ? ctx->m : -1; }
 
 int rqcd_generate(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, uint32_t flags, rqcd_out* out) {
-  if (!ctx || !in || !out || n < 0 || (n > 0 && !in->data) || in->stride < n) return RQCD_ERR_INVALID_ARG;
+  if (!ctx || !out || bad_bc(in, n)) return RQCD_ERR_INVALID_ARG;
   if (out->coeffs && out->coeff_stride < n) return RQCD_ERR_INVALID_ARG;
   if (n == 0) return RQCD_OK;
   DeviceGuard g(ctx->device);
+  CheckParams p = {};
+  p.n = n;
   if (flags & RQCD_F_DEVICE_PTRS) {
-    RQCD_CU(launch_generate(in->data, in->stride, in->goal_mask, n, out->cost, out->coeffs, out->coeff_stride, ctx->stream));
+    bind_bc(p, in);
+    RQCD_CU(launch_generate(p, out->cost, out->coeffs, out->coeff_stride, ctx->stream));
     ctx->launches++;
     return RQCD_OK;
   }
   RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
-  RQCD_CU(rows_h2d(ctx->s_in.p, in->data, in->stride, n, RQCD_BC_ROWS, ctx->stream));
+  BlockList bl;
+  stage_bc(p, bl, in, n, ctx->s_in.p);
+  RQCD_CU(copy_blocks(bl, n, ctx->stream));
   OutStage o;
   if (out->cost) {
     RQCD_CU(ensure(ctx->s_cost, (size_t)n * 8));
@@ -635,7 +643,7 @@ int rqcd_generate(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, uint32_t flag
     o.coeffs = (double*)ctx->s_coeffs.p;
     o.coeff_stride = n;
   }
-  RQCD_CU(launch_generate((const double*)ctx->s_in.p, n, in->goal_mask, n, o.cost, o.coeffs, o.coeff_stride, ctx->stream));
+  RQCD_CU(launch_generate(p, o.cost, o.coeffs, o.coeff_stride, ctx->stream));
   ctx->launches++;
   if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost, o.cost, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (o.coeffs) RQCD_CU(rows_d2h(out->coeffs, out->coeff_stride, o.coeffs, n, RQCD_COEFF_ROWS, ctx->stream));
@@ -645,25 +653,20 @@ int rqcd_generate(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, uint32_t flag
 
 int rqcd_generate_check(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, double min_time_section, uint32_t flags,
                         int64_t index_base, rqcd_out* out) {
-  if (!ctx || !in || n < 0 || (n > 0 && !in->data) || in->stride < n || bad_min_t(min_time_section))
-    return RQCD_ERR_INVALID_ARG;
+  if (!ctx || bad_bc(in, n) || bad_min_t(min_time_section)) return RQCD_ERR_INVALID_ARG;
   int st = validate_out(out, flags, n);
   if (st != RQCD_OK) return st;
   DeviceGuard g(ctx->device);
   CheckCall cc;
   cc.mode = MODE_BC;
-  cc.p.goal_mask = in->goal_mask;
   cc.p.n = n;
   cc.p.index_base = index_base;
   cc.p.min_t = min_time_section;
   if (flags & RQCD_F_DEVICE_PTRS) {
-    cc.p.in = in->data;
-    cc.p.in_stride = in->stride;
+    bind_bc(cc.p, in);
   } else {
     RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
-    cc.add(ctx->s_in.p, in->data, in->stride, RQCD_BC_ROWS);
-    cc.p.in = (const double*)ctx->s_in.p;
-    cc.p.in_stride = n;
+    stage_bc(cc.p, cc, in, n, ctx->s_in.p);
   }
   return finish_check(ctx, cc, out, flags, n, ctx->m, true);
 }
@@ -707,8 +710,7 @@ int rqcd_check(rqcd_ctx* ctx, const rqcd_coeff_soa* in, const double* cost, int6
 
 int rqcd_generate_check_pairwise(rqcd_ctx* ctx, const rqcd_bc_soa* in, const double* spheres, int64_t sphere_stride,
                                  int64_t n, double min_time_section, uint32_t flags, int64_t index_base, rqcd_out* out) {
-  if (!ctx || !in || n < 0 || (n > 0 && (!in->data || !spheres)) || in->stride < n || sphere_stride < n ||
-      bad_min_t(min_time_section))
+  if (!ctx || bad_bc(in, n) || (n > 0 && !spheres) || sphere_stride < n || bad_min_t(min_time_section))
     return RQCD_ERR_INVALID_ARG;
   int st = validate_out(out, flags, n);
   if (st != RQCD_OK) return st;
@@ -717,29 +719,25 @@ int rqcd_generate_check_pairwise(rqcd_ctx* ctx, const rqcd_bc_soa* in, const dou
   CheckCall cc;
   cc.mode = MODE_BC;
   cc.pairwise = true;
-  cc.p.goal_mask = in->goal_mask;
   cc.p.n = n;
   cc.p.index_base = index_base;
   cc.p.min_t = min_time_section;
   if (flags & RQCD_F_DEVICE_PTRS) {
-    cc.p.in = in->data;
-    cc.p.in_stride = in->stride;
+    bind_bc(cc.p, in);
     cc.p.spheres = spheres;
     cc.p.sphere_stride = sphere_stride;
   } else {
     RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
     RQCD_CU(ensure(ctx->s_aux, (size_t)n * 8 * 4));
-    cc.add(ctx->s_in.p, in->data, in->stride, RQCD_BC_ROWS);
+    stage_bc(cc.p, cc, in, n, ctx->s_in.p);
     cc.add(ctx->s_aux.p, spheres, sphere_stride, 4);
-    cc.p.in = (const double*)ctx->s_in.p;
-    cc.p.in_stride = n;
     cc.p.spheres = (const double*)ctx->s_aux.p;
     cc.p.sphere_stride = n;
   }
   return finish_check(ctx, cc, out, flags & ~RQCD_F_EARLY_EXIT, n, 1, true);
 }
 
-static int planes_common(rqcd_ctx* ctx, int mode, CheckParams& p, RowBlock* blocks, int nblocks, int64_t n,
+static int planes_common(rqcd_ctx* ctx, int mode, CheckParams& p, const BlockList& bl, int64_t n,
                          const double* planes, int32_t np, uint32_t flags, uint8_t* verdict, uint8_t* matrix) {
   if (np < 0 || (np > 0 && !planes)) return RQCD_ERR_INVALID_ARG;
   // Boundary.normal = normal.GetUnitVector() (CollisionChecker.cpp:29): float-narrowed norm, Vec3.hpp:117-120
@@ -761,8 +759,7 @@ static int planes_common(rqcd_ctx* ctx, int mode, CheckParams& p, RowBlock* bloc
   const bool dev = flags & RQCD_F_DEVICE_PTRS;
   uint8_t *dv = verdict, *dm = matrix;
   if (!dev) {
-    for (int b = 0; b < nblocks; b++)
-      RQCD_CU(rows_h2d(blocks[b].dst, blocks[b].src, blocks[b].src_stride, n, blocks[b].rows, ctx->stream));
+    RQCD_CU(copy_blocks(bl, n, ctx->stream));
     if (verdict) {
       RQCD_CU(ensure(ctx->s_verdict, (size_t)n));
       dv = (uint8_t*)ctx->s_verdict.p;
@@ -788,8 +785,7 @@ int rqcd_check_planes(rqcd_ctx* ctx, const rqcd_coeff_soa* in, int64_t n, const 
   if (!ctx || !in || n < 0 || (n > 0 && (!in->coeffs || !in->t_end)) || in->stride < n) return RQCD_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
   CheckParams p = {};
-  RowBlock blocks[3];
-  int nb = 0;
+  BlockList bl;
   if (flags & RQCD_F_DEVICE_PTRS) {
     p.in = in->coeffs;
     p.in_stride = in->stride;
@@ -799,59 +795,50 @@ int rqcd_check_planes(rqcd_ctx* ctx, const rqcd_coeff_soa* in, int64_t n, const 
     RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_COEFF_ROWS));
     RQCD_CU(ensure(ctx->s_aux, (size_t)n * 8 * 2));
     double* aux = (double*)ctx->s_aux.p;
-    blocks[nb++] = RowBlock{(double*)ctx->s_in.p, in->coeffs, in->stride, RQCD_COEFF_ROWS};
-    blocks[nb++] = RowBlock{aux, in->t_end, n, 1};
-    if (in->t_start) blocks[nb++] = RowBlock{aux + n, in->t_start, n, 1};
+    bl.add(ctx->s_in.p, in->coeffs, in->stride, RQCD_COEFF_ROWS);
+    bl.add(aux, in->t_end, n, 1);
+    if (in->t_start) bl.add(aux + n, in->t_start, n, 1);
     p.in = (const double*)ctx->s_in.p;
     p.in_stride = n;
     p.t_end = aux;
     p.t_start = in->t_start ? aux + n : nullptr;
   }
-  return planes_common(ctx, MODE_COEFF, p, blocks, nb, n, planes, np, flags, verdict, matrix);
+  return planes_common(ctx, MODE_COEFF, p, bl, n, planes, np, flags, verdict, matrix);
 }
 
 int rqcd_generate_check_planes(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const double* planes, int32_t np,
                                uint32_t flags, uint8_t* verdict, uint8_t* matrix) {
-  if (!ctx || !in || n < 0 || (n > 0 && !in->data) || in->stride < n) return RQCD_ERR_INVALID_ARG;
+  if (!ctx || bad_bc(in, n)) return RQCD_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
   CheckParams p = {};
-  p.goal_mask = in->goal_mask;
-  RowBlock blocks[1];
-  int nb = 0;
+  BlockList bl;
   if (flags & RQCD_F_DEVICE_PTRS) {
-    p.in = in->data;
-    p.in_stride = in->stride;
+    bind_bc(p, in);
   } else {
     RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
-    blocks[nb++] = RowBlock{(double*)ctx->s_in.p, in->data, in->stride, RQCD_BC_ROWS};
-    p.in = (const double*)ctx->s_in.p;
-    p.in_stride = n;
+    stage_bc(p, bl, in, n, ctx->s_in.p);
   }
-  return planes_common(ctx, MODE_BC, p, blocks, nb, n, planes, np, flags, verdict, matrix);
+  return planes_common(ctx, MODE_BC, p, bl, n, planes, np, flags, verdict, matrix);
 }
 
 int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const double* gravity, double fmin,
                            double fmax, double wmax, double min_time_section, const int64_t* group, uint32_t flags,
                            uint8_t* result) {
-  if (!ctx || !in || !gravity || n < 0 || (n > 0 && (!in->data || !result)) || in->stride < n ||
-      bad_min_t(min_time_section))
-    return RQCD_ERR_INVALID_ARG;
+  if (!ctx || !gravity || bad_bc(in, n) || (n > 0 && !result) || bad_min_t(min_time_section)) return RQCD_ERR_INVALID_ARG;
   if (n == 0) return RQCD_OK;
   DeviceGuard g(ctx->device);
   const bool dev = flags & RQCD_F_DEVICE_PTRS;
   CheckParams p = {};
-  p.goal_mask = in->goal_mask;
   p.n = n;
   const long long* dgroup = (const long long*)group;
   uint8_t* dres = result;
   if (dev) {
-    p.in = in->data;
-    p.in_stride = in->stride;
+    bind_bc(p, in);
   } else {
     RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
-    RQCD_CU(rows_h2d(ctx->s_in.p, in->data, in->stride, n, RQCD_BC_ROWS, ctx->stream));
-    p.in = (const double*)ctx->s_in.p;
-    p.in_stride = n;
+    BlockList bl;
+    stage_bc(p, bl, in, n, ctx->s_in.p);
+    RQCD_CU(copy_blocks(bl, n, ctx->stream));
     if (group) {
       RQCD_CU(ensure(ctx->s_group, (size_t)n * 8));
       RQCD_CU(cudaMemcpyAsync(ctx->s_group.p, group, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -873,20 +860,22 @@ int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n
 
 int rqcd_plan_best(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const rqcd_plan_params* prm, uint32_t flags,
                    int64_t index_base, uint8_t* stage, rqcd_summary* summary) {
-  if (!ctx || !in || !prm || !summary || n < 0 || (n > 0 && !in->data) || in->stride < n || bad_min_t(prm->min_time_section) ||
+  if (!ctx || !prm || !summary || bad_bc(in, n) || bad_min_t(prm->min_time_section) ||
       prm->n_planes < 0 || (prm->n_planes > 0 && !prm->planes))
     return RQCD_ERR_INVALID_ARG;
   DeviceGuard g(ctx->device);
   const bool dev = flags & RQCD_F_DEVICE_PTRS;
   cudaStream_t s = ctx->stream;
   // inputs on the device
-  const double* d_bc = in->data;
-  long long stride = in->stride;
-  if (!dev) {
+  CheckParams p = {};
+  p.n = n;
+  if (dev) {
+    bind_bc(p, in);
+  } else {
     RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * RQCD_BC_ROWS));
-    RQCD_CU(rows_h2d(ctx->s_in.p, in->data, in->stride, n, RQCD_BC_ROWS, s));
-    d_bc = (const double*)ctx->s_in.p;
-    stride = n;
+    BlockList bl;
+    stage_bc(p, bl, in, n, ctx->s_in.p);
+    RQCD_CU(copy_blocks(bl, n, s));
   }
   // scratch: cost, feasibility, plane hits, stage, verdict
   RQCD_CU(ensure(ctx->s_cost, (size_t)(n > 0 ? n : 1) * 8));
@@ -898,13 +887,8 @@ int rqcd_plan_best(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const rqcd_p
   uint8_t* d_stage_scratch = d_feas + 2 * n;
   uint8_t* d_stage = (dev && stage) ? stage : d_stage_scratch;
   uint8_t* d_verdict = (uint8_t*)ctx->s_verdict.p;
-  CheckParams p = {};
-  p.in = d_bc;
-  p.in_stride = stride;
-  p.goal_mask = in->goal_mask;
-  p.n = n;
   // stage 0: Generate + GetCost
-  RQCD_CU(launch_generate(d_bc, stride, in->goal_mask, n, d_cost, nullptr, 0, s));
+  RQCD_CU(launch_generate(p, d_cost, nullptr, 0, s));
   ctx->launches += n > 0;
   // stage 1: CheckInputFeasibility
   if (prm->check_input && n > 0) {

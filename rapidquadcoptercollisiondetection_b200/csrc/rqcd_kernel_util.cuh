@@ -79,19 +79,37 @@ RQCD_DEV bool wait_for_input(const CheckParams& p, unsigned long long want, unsi
   return ok != 0;
 }
 
+// ---- boundary-condition rows (rqcd_bc_soa) ---------------------------------------------------------------
+// Where candidate i of the launch finds its element: in a per-candidate row, in a shared (per-group) row.
+struct BcIndex {
+  long long cand, grp;
+};
+RQCD_DEV BcIndex bc_index(const CheckParams& p, long long i) {
+  BcIndex x;
+  x.cand = i + p.in_first;
+  x.grp = 0;
+  if (p.shared_rows != 0u) {
+    const unsigned long long q = (unsigned long long)(i + p.grp_first), g = (unsigned long long)p.group_size;
+    x.grp = (long long)(((q | g) >> 32) == 0 ? (unsigned long long)((unsigned)q / (unsigned)g) : q / g);
+  }
+  return x;
+}
+RQCD_DEV double bc_at(const CheckParams& p, int r, const BcIndex& x) {
+  return ld_in(p.in + r * p.in_stride + (((p.shared_rows >> r) & 1u) ? x.grp : x.cand));
+}
+
 // ---- trajectory construction for one lane ------------------------------------------------------------
 template <int MODE>
 RQCD_DEV void load_trajectory(const CheckParams& p, long long i, double (&c)[18], double& t0, double& t1,
                               double& cost) {
   if (MODE == MODE_BC) {
-    const double* d = p.in;
-    const long long s = p.in_stride;
-    const double Tf = ld_in(d + 18 * s + i);
+    const BcIndex x = bc_index(p, i);
+    const double Tf = bc_at(p, 18, x);
     double total = 0.0;
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
-      const double p0 = ld_in(d + (0 + ax) * s + i), v0 = ld_in(d + (3 + ax) * s + i), a0 = ld_in(d + (6 + ax) * s + i);
-      const double pf = ld_in(d + (9 + ax) * s + i), vf = ld_in(d + (12 + ax) * s + i), af = ld_in(d + (15 + ax) * s + i);
+      const double p0 = bc_at(p, 0 + ax, x), v0 = bc_at(p, 3 + ax, x), a0 = bc_at(p, 6 + ax, x);
+      const double pf = bc_at(p, 9 + ax, x), vf = bc_at(p, 12 + ax, x), af = bc_at(p, 15 + ax, x);
       const AxisParams q = gen_axis(p0, v0, a0, pf, vf, af, (p.goal_mask >> (3 * ax)) & 1,
                                     (p.goal_mask >> (3 * ax + 1)) & 1, (p.goal_mask >> (3 * ax + 2)) & 1, Tf);
       axis_coeffs(q, p0, v0, a0, c[0 + ax], c[3 + ax], c[6 + ax], c[9 + ax], c[12 + ax], c[15 + ax]);

@@ -150,11 +150,10 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
           if (lane < 3 * kCoopOwners && q < n_own) {
             const unsigned own = __fns(owners, 0, q + 1);
             const long long i = (long long)b + __popc(need & ((1u << own) - 1u));
-            const double* d = p.in;
-            const long long st = p.in_stride;
-            const double Tf = ld_in(d + 18 * st + i);
-            const double p0 = ld_in(d + (0 + ax) * st + i), v0 = ld_in(d + (3 + ax) * st + i), a0 = ld_in(d + (6 + ax) * st + i);
-            const double pf = ld_in(d + (9 + ax) * st + i), vf = ld_in(d + (12 + ax) * st + i), af = ld_in(d + (15 + ax) * st + i);
+            const BcIndex x = bc_index(p, i);
+            const double Tf = bc_at(p, 18, x);
+            const double p0 = bc_at(p, 0 + ax, x), v0 = bc_at(p, 3 + ax, x), a0 = bc_at(p, 6 + ax, x);
+            const double pf = bc_at(p, 9 + ax, x), vf = bc_at(p, 12 + ax, x), af = bc_at(p, 15 + ax, x);
             const AxisParams g = gen_axis(p0, v0, a0, pf, vf, af, (p.goal_mask >> (3 * ax)) & 1,
                                           (p.goal_mask >> (3 * ax + 1)) & 1, (p.goal_mask >> (3 * ax + 2)) & 1, Tf);
             axis_coeffs(g, p0, v0, a0, tc[0], tc[1], tc[2], tc[3], tc[4], tc[5]);
@@ -471,13 +470,39 @@ __global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int
   }
 }
 
+// ---- multi-GPU exchange (rqcd_multi_*): a shard's summary goes to its slot of a table on the first device -- a store
+// through peer-mapped memory (NVLink) or zero-copy host memory -- and one thread block there merges the table with
+// rqcd_merge_summaries' rule: counts add; best = lowest cost, lowest index on ties (identical for every shard count).
+__global__ void k_publish_summary(const DevSummary* mine, DevSummary* slot) {
+  if (threadIdx.x == 0) {
+    *slot = *mine;
+    __threadfence_system();
+  }
+}
+__global__ void k_merge_summaries(const DevSummary* slots, int n, DevSummary* out, DevSummary* copy) {
+  if (threadIdx.x != 0) return;
+  DevSummary m = {};
+  m.best_cost = __longlong_as_double(0x7ff0000000000000ll);
+  m.best_index = -1;
+  for (int k = 0; k < n; k++) {
+    const DevSummary s = slots[k];
+    for (int v = 0; v < 4; v++) {
+      m.traj[v] += s.traj[v];
+      m.pair[v] += s.pair[v];
+    }
+    m.pairs_checked += s.pairs_checked;
+    if (better(s.best_cost, s.best_index, m.best_cost, m.best_index)) {
+      m.best_cost = s.best_cost;
+      m.best_index = s.best_index;
+    }
+  }
+  *out = m;
+  if (copy) *copy = m;
+}
+
 // ---- RapidTrajectoryGenerator::Generate + GetCost + GetTrajectory only --------------------------------
-__global__ void __launch_bounds__(256) k_generate(const double* bc, long long stride, unsigned goal_mask, long long n,
-                                                  double* cost, double* coeffs, long long coeff_stride) {
-  CheckParams p = {};
-  p.in = bc;
-  p.in_stride = stride;
-  p.goal_mask = goal_mask;
+__global__ void __launch_bounds__(256) k_generate(const CheckParams p, double* cost, double* coeffs, long long coeff_stride) {
+  const long long n = p.n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double c[18], t0, t1, co;
     load_trajectory<MODE_BC>(p, i, c, t0, t1, co);
@@ -530,13 +555,12 @@ __global__ void __launch_bounds__(256) k_planes(const CheckParams p, const doubl
 
 // ---- RapidTrajectoryGenerator::CheckInputFeasibility (src/RapidTrajectoryGenerator.cpp:74-160) --------------------
 RQCD_DEV void feas_axes(const CheckParams& p, long long i, AxisState (&ax)[3], double& Tf) {
-  const double* d = p.in;
-  const long long s = p.in_stride;
-  Tf = d[18 * s + i];
+  const BcIndex x = bc_index(p, i);
+  Tf = bc_at(p, 18, x);
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    const double p0 = d[(0 + k) * s + i], v0 = d[(3 + k) * s + i], a0 = d[(6 + k) * s + i];
-    const AxisParams q = gen_axis(p0, v0, a0, d[(9 + k) * s + i], d[(12 + k) * s + i], d[(15 + k) * s + i],
+    const double p0 = bc_at(p, 0 + k, x), v0 = bc_at(p, 3 + k, x), a0 = bc_at(p, 6 + k, x);
+    const AxisParams q = gen_axis(p0, v0, a0, bc_at(p, 9 + k, x), bc_at(p, 12 + k, x), bc_at(p, 15 + k, x),
                                   (p.goal_mask >> (3 * k)) & 1, (p.goal_mask >> (3 * k + 1)) & 1,
                                   (p.goal_mask >> (3 * k + 2)) & 1, Tf);
     ax[k].a0 = a0;
@@ -760,6 +784,15 @@ const void* select_check(int mode, bool moving, bool pairwise, int m) {
   return mode == MODE_BC ? check_fn<MODE_BC, false, false, false>() : check_fn<MODE_COEFF, false, false, false>();
 }
 
+// SMs of the current device (the caller's DeviceGuard has selected the context's GPU): grid caps are multiples of it
+int sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      sms < 1)
+    sms = 148;  // B200
+  return sms;
+}
+
 int grid_for(long long n, int cap) {
   long long b = (n + 255) / 256;
   if (b < 1) b = 1;
@@ -821,6 +854,15 @@ cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairw
   return cudaLaunchKernel(select_check(mode, moving, pairwise, p.m), dim3(grid), dim3(kThreads), args, smem, s);
 }
 
+cudaError_t launch_publish_summary(const DevSummary* mine, DevSummary* slot, cudaStream_t s) {
+  k_publish_summary<<<1, 32, 0, s>>>(mine, slot);
+  return cudaGetLastError();
+}
+cudaError_t launch_merge_summaries(const DevSummary* slots, int n, DevSummary* out, DevSummary* copy, cudaStream_t s) {
+  k_merge_summaries<<<1, 32, 0, s>>>(slots, n, out, copy);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_finalize(const BlockPartial* partials, int grid, DevSummary* d_summary, cudaStream_t s) {
   k_finalize<<<1, 256, 0, s>>>(partials, grid, d_summary);
   return cudaGetLastError();
@@ -829,7 +871,7 @@ cudaError_t launch_finalize(const BlockPartial* partials, int grid, DevSummary* 
 cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, int np, uint8_t* verdict, uint8_t* matrix,
                           cudaStream_t s) {
   if (p.n <= 0) return cudaSuccess;
-  const int grid = grid_for(p.n, 148 * 8);
+  const int grid = grid_for(p.n, sm_count() * 8);
   if (mode == MODE_BC) k_planes<MODE_BC><<<grid, 256, 0, s>>>(p, planes, np, verdict, matrix);
   else k_planes<MODE_COEFF><<<grid, 256, 0, s>>>(p, planes, np, verdict, matrix);
   return cudaGetLastError();
@@ -841,7 +883,7 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
   FeasArgs fa;
   for (int k = 0; k < 3; k++) fa.grav[k] = grav[k];
   fa.fmin = fmin, fa.fmax = fmax, fa.wmax = wmax, fa.min_t = min_t;
-  const int grid = (int)((p.n + 127) / 128 < 148 * 16 ? (p.n + 127) / 128 : 148 * 16);
+  const int grid = (int)((p.n + 127) / 128 < sm_count() * 16 ? (p.n + 127) / 128 : sm_count() * 16);
   if (group) {
     k_feas_group_peaks<<<grid, 128, 0, s>>>(p, fa, group, peaks);
     cudaError_t e = cudaGetLastError();
@@ -854,32 +896,31 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
 cudaError_t launch_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas, const uint8_t* plane_hit,
                              uint8_t* stage, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_plan_mask<<<grid_for(n, 148 * 8), 256, 0, s>>>(n, cost, max_cost, feas, plane_hit, stage);
+  k_plan_mask<<<grid_for(n, sm_count() * 8), 256, 0, s>>>(n, cost, max_cost, feas, plane_hit, stage);
   return cudaGetLastError();
 }
 cudaError_t launch_plan_stage(long long n, const uint8_t* verdict, uint8_t* stage, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_plan_stage<<<grid_for(n, 148 * 8), 256, 0, s>>>(n, verdict, stage);
+  k_plan_stage<<<grid_for(n, sm_count() * 8), 256, 0, s>>>(n, verdict, stage);
   return cudaGetLastError();
 }
 
-cudaError_t launch_generate(const double* bc, long long stride, unsigned goal_mask, long long n, double* cost,
-                            double* coeffs, long long coeff_stride, cudaStream_t s) {
-  if (n <= 0) return cudaSuccess;
-  k_generate<<<grid_for(n, 148 * 8), 256, 0, s>>>(bc, stride, goal_mask, n, cost, coeffs, coeff_stride);
+cudaError_t launch_generate(const CheckParams& p, double* cost, double* coeffs, long long coeff_stride, cudaStream_t s) {
+  if (p.n <= 0) return cudaSuccess;
+  k_generate<<<grid_for(p.n, sm_count() * 8), 256, 0, s>>>(p, cost, coeffs, coeff_stride);
   return cudaGetLastError();
 }
 
 cudaError_t launch_solve(bool quartic, const double* coef, long long n, double* roots, int* count, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_solve<<<grid_for(n, 148 * 8), 256, 0, s>>>(quartic, coef, n, roots, count);
+  k_solve<<<grid_for(n, sm_count() * 8), 256, 0, s>>>(quartic, coef, n, roots, count);
   return cudaGetLastError();
 }
 
 cudaError_t launch_synth_bc(unsigned long long seed, long long index_base, long long n, double* bc, long long stride,
                             cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_synth_bc<<<grid_for(n, 148 * 8), 256, 0, s>>>(seed, index_base, n, bc, stride);
+  k_synth_bc<<<grid_for(n, sm_count() * 8), 256, 0, s>>>(seed, index_base, n, bc, stride);
   return cudaGetLastError();
 }
 

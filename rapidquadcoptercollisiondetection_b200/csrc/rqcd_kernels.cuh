@@ -37,6 +37,11 @@ struct CheckParams {
   // trajectories
   const double* in;        // MODE_BC: 19 boundary-condition rows; MODE_COEFF: 18 coefficient rows
   long long in_stride;
+  // MODE_BC, rqcd_bc_soa::shared_rows: bit r set = row r holds one value per GROUP of group_size consecutive candidates.
+  // Candidate i of the launch reads element i + in_first of a per-candidate row and element (i + grp_first) / group_size
+  // of a shared row (see bc_index in rqcd_kernel_util.cuh).
+  unsigned shared_rows;
+  long long in_first, grp_first, group_size;
   const double* t_start;   // MODE_COEFF, may be null (0)
   const double* t_end;     // MODE_COEFF
   const double* cost_in;   // MODE_COEFF, may be null (NaN)
@@ -85,6 +90,10 @@ cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t sm
 const char* check_kernel_name(bool moving, bool pairwise, int m);
 constexpr int kEndBitsMinObstacles = 16;  // static tables at least this long: end-point tests as a pre-pass
 cudaError_t launch_finalize(const BlockPartial* partials, int grid, DevSummary* d_summary, cudaStream_t s);
+// multi-GPU exchange (rqcd_multi.cu): a shard's summary to its slot of a table (peer-mapped memory of the group's first
+// device, or the all-gather's receive buffer); the merge of all slots into *out (and *copy when given)
+cudaError_t launch_publish_summary(const DevSummary* mine, DevSummary* slot, cudaStream_t s);
+cudaError_t launch_merge_summaries(const DevSummary* slots, int n, DevSummary* out, DevSummary* copy, cudaStream_t s);
 
 // ---- k_pool (rqcd_pool.cu): staged sections with the certified solver skip; obstacle tables, static or moving
 size_t pool_smem_bytes(int mp, int stride, int threads);
@@ -103,8 +112,7 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
 cudaError_t launch_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas, const uint8_t* plane_hit,
                              uint8_t* stage, cudaStream_t s);
 cudaError_t launch_plan_stage(long long n, const uint8_t* verdict, uint8_t* stage, cudaStream_t s);
-cudaError_t launch_generate(const double* bc, long long stride, unsigned goal_mask, long long n, double* cost,
-                            double* coeffs, long long coeff_stride, cudaStream_t s);
+cudaError_t launch_generate(const CheckParams& p, double* cost, double* coeffs, long long coeff_stride, cudaStream_t s);
 cudaError_t launch_solve(bool quartic, const double* coef, long long n, double* roots, int* count, cudaStream_t s);
 cudaError_t launch_synth_bc(unsigned long long seed, long long index_base, long long n, double* bc, long long stride,
                             cudaStream_t s);

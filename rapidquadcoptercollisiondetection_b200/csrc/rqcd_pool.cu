@@ -94,15 +94,13 @@ __device__ __noinline__ AxisOut gen_axis_out(double p0, double v0, double a0, do
 template <int MODE>
 RQCD_DEV void load_trajectory_compact(const CheckParams& p, long long i, double (&c)[18], double& t0, double& t1, double& cost) {
   if (MODE == MODE_BC) {
-    const double* d = p.in;
-    const long long s = p.in_stride;
-    const double Tf = ld_in(d + 18 * s + i);
+    const BcIndex x = bc_index(p, i);
+    const double Tf = bc_at(p, 18, x);
     double total = 0.0;
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
-      const AxisOut q = gen_axis_out(ld_in(d + (0 + ax) * s + i), ld_in(d + (3 + ax) * s + i), ld_in(d + (6 + ax) * s + i),
-                                     ld_in(d + (9 + ax) * s + i), ld_in(d + (12 + ax) * s + i), ld_in(d + (15 + ax) * s + i),
-                                     (p.goal_mask >> (3 * ax)) & 7u, Tf);
+      const AxisOut q = gen_axis_out(bc_at(p, 0 + ax, x), bc_at(p, 3 + ax, x), bc_at(p, 6 + ax, x), bc_at(p, 9 + ax, x),
+                                     bc_at(p, 12 + ax, x), bc_at(p, 15 + ax, x), (p.goal_mask >> (3 * ax)) & 7u, Tf);
 #pragma unroll
       for (int j = 0; j < 6; j++) c[3 * j + ax] = q.k[j];
       total = (ax == 0) ? q.cost : total + q.cost;  // GetCost: cost[0] + cost[1] + cost[2] (.hpp:214-216)

@@ -31,7 +31,7 @@ def test_struct_mirrors_match_header_sizes():
     # rqcd_obstacle: 2 x int32 + (3+1+3+4+18+2) doubles; rqcd_summary: 9 x 8 bytes + double + int64
     assert C.sizeof(abi.Obstacle) == 8 + 31 * 8
     assert C.sizeof(abi.Summary) == 11 * 8
-    assert C.sizeof(abi.BcSoa) == 24 and C.sizeof(abi.CoeffSoa) == 32 and C.sizeof(abi.Out) == 56
+    assert C.sizeof(abi.BcSoa) == 40 and C.sizeof(abi.CoeffSoa) == 32 and C.sizeof(abi.Out) == 56
 
 
 def test_no_device_means_no_service():
@@ -58,3 +58,18 @@ def test_merge_summaries_is_the_only_exchange_step():
     assert m["best_cost"] == 3.5 and m["best_index"] == 3  # tie on cost -> lowest index
     e = merge_summaries([])
     assert e["best_index"] == -1 and e["best_cost"] == inf and e["pairs_checked"] == 0
+
+
+def test_shard_range_matches_the_python_host_logic():
+    from rapidquadcoptercollisiondetection_b200 import sharding
+    lib = abi.load()
+    for n in (0, 1, 7, 1000, (1 << 26) + 5, 1 << 40):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for k in range(world):
+                lo, hi = C.c_int64(), C.c_int64()
+                lib.rqcd_shard_range(n, k, world, C.byref(lo), C.byref(hi))
+                assert (lo.value, hi.value) == sharding.shard_range(n, k, world)
+                assert lo.value == prev
+                prev = hi.value
+            assert prev == n
