@@ -197,7 +197,8 @@ def run_cpu(impl, name, obs, m, bc, sph, threads):
 
 
 def reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path on the box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, on the SAME
+    configuration as the b200 arm (the whole per-rank batch of the workload per step; c5: a bounded prefix)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -209,8 +210,9 @@ def reference_arm(args):
     gen = lambda b: impl.generate(b)["coeffs"]  # noqa: E731
     specs, obs = build_obstacles(name, W, abi, gen)
     m = max(len(specs), 1)
-    # bounded sample of the same workload: ~1.6e7 pair checks per step
-    n_s = max(1024, min(w["n"], (1 << 24) // m))
+    # the full per-rank batch while a step stays below ~2^27 pair checks (c3: all 2^20 x 64 = 6.7e7, ~1.5 s on 16
+    # threads); a prefix of it otherwise (c5)
+    n_s = max(1024, min(w["n"], (1 << 27) // m))
     bc, sph = host_inputs(name, W, 0, n_s)
     times, pairs = [], 0
     for it in range(args.warmup + args.steps):
@@ -220,17 +222,274 @@ def reference_arm(args):
             pairs += r["summary"]["pairs_checked"]
     total = sum(times)
     value = pairs / total
-    sample = f"first {n_s} candidates of {name} x {len(specs) if name != 'c1' else 1} obstacles per step"
+    whole = n_s == w["n"]
+    sample = (f"all {n_s} candidates" if whole else f"first {n_s} candidates") + f" of {name} x {len(specs) if name != 'c1' else 1} obstacles per step"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
         "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{name}: {w['desc']}", "sample": sample, "min_time_section": MIN_T},
+        "config": {"workload": f"{name}: {w['desc']}", "candidates_per_rank": n_s, "obstacles": len(specs) if name != "c1" else 1,
+                   "min_time_section": MIN_T, "sample": sample},
+        "trajectories_per_sec": value / (len(specs) if name not in ("c1", "c2") and specs else 1) if name != "c2" else n_s * args.steps / total,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the b200 arm
+# ---------------------------------------------------------------------------------------------------------
+RECORD_WORDS = 11  # rqcd_summary as int64 words: traj[4], pair[4], pairs_checked, best_cost (bits), best_index
+P0_ROWS = (0, 1, 2)
+FOREST_SHARED = (0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 13, 14, 15, 16, 17)
+
+
+def record_to_summary(rec) -> dict:
+    rec = np.asarray(rec, dtype=np.int64)
+    return {"traj_counts": [int(x) for x in rec[0:4]], "pair_counts": [int(x) for x in rec[4:8]],
+            "pairs_checked": int(rec[8]), "best_cost": float(rec[9:10].view(np.float64)[0]), "best_index": int(rec[10])}
+
+
+class Rig:
+    """One rank: its GPU, its context (with the NCCL communicator of the in-library exchange when world > 1), its stream."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from rapidquadcoptercollisiondetection_b200.api import Context, comm_unique_id
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the path has no CPU implementation in this repo")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)  # plumbing: rendezvous, barriers, max over ranks
+        self.ctx = Context(self.local)
+        self.stream = torch.cuda.Stream(self.dev)  # the one stream everything is launched and timed on
+        torch.cuda.set_stream(self.stream)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        if self.world > 1:
+            # the data-path exchange is the library's own: a context-owned communicator; the id travels over torch's
+            ident = torch.zeros(128, dtype=torch.uint8, device=self.dev)
+            if self.rank == 0:
+                ident.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(ident, 0)
+            self.ctx.comm_init(bytes(ident.cpu().numpy().tobytes()), self.rank, self.world)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.ctx.comm_finalize()
+        self.ctx.close()
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+class Resident:
+    """A workload with its inputs resident in HBM on this rank."""
+
+    def __init__(self, rig: Rig, name: str):
+        from rapidquadcoptercollisiondetection_b200 import abi, sharding, workloads as W
+        torch = rig.torch
+        self.rig, self.name, self.w = rig, name, WORKLOADS[name]
+        w = self.w
+        self.n_global = w["n"] if w["scaling"] == "strong" else w["n"] * rig.world
+        self.lo, self.hi = sharding.shard_range(self.n_global, rig.rank, rig.world)
+        self.n = n = self.hi - self.lo
+        self.specs, self.obs = build_obstacles(name, W, abi, lambda b: rig.ctx.generate(b)["coeffs"])
+        self.m = len(self.specs)
+        if name != "c1":
+            rig.ctx.set_obstacles(self.obs, self.m)
+        self.pairs_per_traj = 1 if name == "c1" else self.m
+        self.flags = abi.F_EARLY_EXIT if name == "c2" else 0
+        self.d_bc = torch.empty((abi.BC_ROWS, n), dtype=torch.float64, device=rig.dev)
+        self.d_sph = None
+        self.bc_h = self.sph_h = None
+        if name in ("c2", "c1"):
+            self.bc_h, self.sph_h = host_inputs(name, W, self.lo, n)
+            self.d_bc.copy_(torch.from_numpy(self.bc_h))
+            if self.sph_h is not None:
+                self.d_sph = torch.from_numpy(self.sph_h).to(rig.dev)
+        else:
+            rig.ctx.synth_bc(w["seed"], self.lo, n, self.d_bc.data_ptr(), n)  # on the device from (seed, global index)
+        self.d_verdict = torch.empty(n, dtype=torch.uint8, device=rig.dev)
+        self.d_first = torch.empty(n, dtype=torch.int32, device=rig.dev)
+        self.d_cost = torch.empty(n, dtype=torch.float64, device=rig.dev)
+        torch.cuda.synchronize(rig.dev)
+
+    def enqueue(self, d_record: int):
+        """One step: the check launch (+ k_finalize) and the exchange (all-gather + merge), all on the stream, no host sync."""
+        ctx = self.rig.ctx
+        if self.name == "c1":
+            ctx.generate_check_pairwise_dev(self.d_bc.data_ptr(), self.n, self.d_sph.data_ptr(), self.n, self.n, MIN_T,
+                                            index_base=self.lo, d_verdict=self.d_verdict.data_ptr(), d_cost=self.d_cost.data_ptr())
+        else:
+            ctx.generate_check_dev(self.d_bc.data_ptr(), self.n, self.n, MIN_T, flags=self.flags, index_base=self.lo,
+                                   d_verdict=self.d_verdict.data_ptr(), d_first=self.d_first.data_ptr(),
+                                   d_cost=self.d_cost.data_ptr())
+        ctx.exchange_summaries(d_record)
+
+    def time_steps(self, steps: int, warmup: int, clocks: bool = True) -> dict:
+        """Device-timed: W warm-up steps, then K steps bracketed by barrier + synchronize; the K merged records land in a
+        device ring that is read once after the timed region."""
+        rig, torch = self.rig, self.rig.torch
+        ring = torch.zeros((max(steps, warmup), RECORD_WORDS), dtype=torch.int64, device=rig.dev)
+        for k in range(warmup):
+            self.enqueue(ring[k].data_ptr())
+        rig.barrier()
+        launches0 = rig.ctx.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(rig.local) if clocks else None
+        if sampler:
+            sampler.__enter__()
+        rig.barrier()
+        ev0.record(rig.stream)
+        for k in range(steps):
+            self.enqueue(ring[k].data_ptr())
+        ev1.record(rig.stream)
+        rig.barrier()
+        if sampler:
+            sampler.__exit__()
+        ms = rig.max_over_ranks(ev0.elapsed_time(ev1))
+        recs = ring[:steps].cpu().numpy()
+        assert (recs == recs[0]).all(), "the merged record must be the same every step"
+        summary = record_to_summary(recs[0])
+        pairs_total = int(recs[:, 8].sum())
+        return {"ms": ms, "ms_per_step": ms / steps, "value": pairs_total / (ms * 1e-3), "pairs_total": pairs_total,
+                "summary": summary, "launches": int(rig.ctx.launch_count() - launches0), "kernel": rig.ctx.last_kernel_name(),
+                "clocks": sampler.summary() if sampler else None,
+                "trajectories_per_sec": self.n_global * steps / (ms * 1e-3)}
+
+    def time_e2e(self, steps: int) -> dict:
+        """End to end through the host-pointer C-ABI call: pinned HOST buffers in, verdicts / first hits / costs and the merged
+        summary back on the host every step. Rows every candidate shares are shipped once per group (rqcd_bc_soa::shared_rows):
+        the drivers' constant pos0 (PerformanceEval.cpp:76), and for the Forest workload the batch's initial state and the zero
+        goal velocity / acceleration (ForestPerformanceEval.cpp:175-193)."""
+        import ctypes as C
+
+        from rapidquadcoptercollisiondetection_b200 import abi
+        from rapidquadcoptercollisiondetection_b200.api import shared_row_mask
+        rig, torch, name = self.rig, self.rig.torch, self.name
+        ne = min(self.n, 1 << 22)  # the whole shard when it is at most 2^22 candidates; a prefix of it otherwise (c5)
+        bc_host = torch.zeros((abi.BC_ROWS, ne), dtype=torch.float64).pin_memory()
+        sph_host = None
+        if name == "c2":
+            shared, group = FOREST_SHARED, 100
+            full = torch.from_numpy(np.ascontiguousarray(self.bc_h[:, :ne]))
+            ng = (ne + group - 1) // group
+            for r in range(abi.BC_ROWS):
+                if r in shared:
+                    bc_host[r, :ng] = full[r, ::group]
+                else:
+                    bc_host[r] = full[r]
+        else:
+            shared, group = P0_ROWS, max(ne, 1)
+            bc_host.copy_(self.d_bc[:, :ne])
+            if name == "c1":
+                sph_host = torch.from_numpy(np.ascontiguousarray(self.sph_h[:, :ne])).pin_memory()
+        mask = shared_row_mask(shared)
+        ng = (ne + group - 1) // group
+        v_host = torch.empty(ne, dtype=torch.uint8).pin_memory()
+        f_host = torch.empty(ne, dtype=torch.int32).pin_memory()
+        c_host = torch.empty(ne, dtype=torch.float64).pin_memory()
+        summ = abi.Summary()
+        lib, ctx = rig.ctx.lib, rig.ctx
+
+        def step_host():
+            inp = abi.BcSoa(bc_host.data_ptr(), ne, abi.GOAL_ALL, mask, group, 0)
+            if name == "c1":
+                out = abi.Out(verdict=v_host.data_ptr(), cost=c_host.data_ptr(), summary=C.pointer(summ))
+                st = lib.rqcd_generate_check_pairwise(ctx.h, C.byref(inp), sph_host.data_ptr(), ne, ne, MIN_T, 0, self.lo, C.byref(out))
+            else:
+                out = abi.Out(verdict=v_host.data_ptr(), first_obstacle=f_host.data_ptr(), cost=c_host.data_ptr(),
+                              summary=C.pointer(summ))
+                st = lib.rqcd_generate_check(ctx.h, C.byref(inp), ne, MIN_T, self.flags, self.lo, C.byref(out))
+            assert st == abi.OK, st
+            ctx.exchange_summaries()
+            return ctx.read_merged_summary()  # the step's result on the host
+
+        for _ in range(3):
+            step_host()
+        rig.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(rig.stream)
+        pairs = 0
+        for _ in range(steps):
+            pairs += step_host()["pairs_checked"]
+        ev1.record(rig.stream)
+        rig.barrier()
+        ms = rig.max_over_ranks(ev0.elapsed_time(ev1))
+        n_per = abi.BC_ROWS - len(shared)
+        h2d = (n_per * ne + len(shared) * ng) * 8 + (4 * ne * 8 if name == "c1" else 0)
+        d2h = ne * (1 + 8) + (0 if name == "c1" else 4 * ne) + 88
+        return {"value": pairs / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms / steps, "steps": steps, "candidates_per_rank_per_step": ne,
+                "input_layout": f"{n_per} rows per candidate + {len(shared)} rows per group of {group} (rqcd_bc_soa shared_rows)",
+                "trajectories_per_sec": ne * rig.world * steps / (ms * 1e-3)}
+
+
+def traffic_for(kernel: str, name: str):
+    """DRAM bytes of one launch from the committed ncu capture of THIS kernel on THIS workload, else None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[name]
+    except Exception:
+        return None, None
+    if rec.get("kernel") != kernel:
+        return None, f"no capture of {kernel} on {name} (profiles/ncu_traffic.json has {rec.get('kernel')})"
+    return rec["dram_bytes_per_launch"], rec.get("source")
+
+
+def c5_block(rig: Rig, steps: int) -> dict:
+    """BASELINE config 5 (2^26 x 256, strong scaling, best-candidate reduce) beside the headline workload: a few steps,
+    the merged record checked against the committed single-GPU expectation and, on rank 0, every 1024-th candidate of the
+    shard against the oracle."""
+    from rapidquadcoptercollisiondetection_b200 import workloads as W
+    res = Resident(rig, "c5")
+    t = res.time_steps(steps, 3, clocks=False)
+    out = {"workload": f"c5: {WORKLOADS['c5']['desc']}", "value": t["value"], "unit": UNIT, "ms_per_step": t["ms_per_step"],
+           "steps": steps, "scaling": "strong", "candidates_per_rank": res.n, "kernel": t["kernel"], "summary": t["summary"],
+           "trajectories_per_sec": t["trajectories_per_sec"]}
+    try:
+        exp = json.load(open(os.path.join(ROOT, "tests", "golden", "c5_expected.json")))
+        s = t["summary"]
+        out["matches_expected"] = (s["traj_counts"] == exp["traj_counts"] and s["pair_counts"] == exp["pair_counts"] and
+                                   s["best_index"] == exp["best_index"] and s["best_cost"] == exp["best_cost"])
+    except FileNotFoundError:
+        out["matches_expected"] = None
+    if rig.rank == 0:
+        from oracle import binding as B
+        first = (res.lo + 1023) // 1024 * 1024
+        idx = np.arange(first, res.hi, 1024, dtype=np.int64)
+        bc = W.synth_bc_at(WORKLOADS["c5"]["seed"], idx)
+        o = B.Oracle().generate_check(bc, res.obs, res.m, MIN_T, matrix=False, nthreads=os.cpu_count() or 1)
+        got_v = res.d_verdict[torch_index(rig, idx - res.lo)].cpu().numpy()
+        got_f = res.d_first[torch_index(rig, idx - res.lo)].cpu().numpy()
+        out["oracle_sample"] = int(len(idx))
+        out["oracle_mismatches"] = int((got_v != o["verdict"]).sum() + (got_f != o["first_obstacle"]).sum())
+    del res
+    rig.torch.cuda.empty_cache()
+    return out
+
+
+def torch_index(rig: Rig, idx):
+    return rig.torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(rig.dev)
 
 
 def main():
@@ -242,6 +501,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c5 / feasibility / planner blocks")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -249,163 +509,33 @@ def main():
         reference_arm(args)
         return
 
-    import torch
-    import torch.distributed as dist
+    from rapidquadcoptercollisiondetection_b200 import workloads as W
 
-    from rapidquadcoptercollisiondetection_b200 import abi, sharding, workloads as W
-    from rapidquadcoptercollisiondetection_b200.api import Context
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the path has no CPU implementation in this repo")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    rig = Rig()
+    rank, world = rig.rank, rig.world
     name = args.workload
     w = WORKLOADS[name]
-    n_global = w["n"] if w["scaling"] == "strong" else w["n"] * world
-    lo, hi = sharding.shard_range(n_global, rank, world)
-    n = hi - lo
+    res = Resident(rig, name)
+    n, m, pairs_per_traj = res.n, res.m, res.pairs_per_traj
 
-    ctx = Context(local)
-    stream = torch.cuda.Stream(dev)  # the one stream everything is launched and timed on
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-    specs, obs = build_obstacles(name, W, abi, lambda b: ctx.generate(b)["coeffs"])
-    m = len(specs)
-    if name != "c1":
-        ctx.set_obstacles(obs, m)
-    pairs_per_traj = 1 if name == "c1" else m
-    flags = abi.F_EARLY_EXIT if name == "c2" else 0
-
-    # ---- inputs resident in HBM -------------------------------------------------------------------------
-    d_bc = torch.empty((abi.BC_ROWS, n), dtype=torch.float64, device=dev)
-    d_sph = None
-    if name in ("c2", "c1"):
-        bc_h, sph_h = host_inputs(name, W, lo, n)
-        d_bc.copy_(torch.from_numpy(bc_h))
-        if sph_h is not None:
-            d_sph = torch.from_numpy(sph_h).to(dev)
-    else:
-        ctx.synth_bc(w["seed"], lo, n, d_bc.data_ptr(), n)  # generated on the device from (seed, global index)
-    d_verdict = torch.empty(n, dtype=torch.uint8, device=dev)
-    d_first = torch.empty(n, dtype=torch.int32, device=dev)
-    d_cost = torch.empty(n, dtype=torch.float64, device=dev)
-    torch.cuda.synchronize(dev)
-
-    gather_buf = torch.zeros((world, 11), dtype=torch.int64, device=dev) if world > 1 else None
-
-    def step_device():
-        if name == "c1":
-            s = ctx.generate_check_pairwise_dev(d_bc.data_ptr(), n, d_sph.data_ptr(), n, n, MIN_T, index_base=lo,
-                                                d_verdict=d_verdict.data_ptr(), d_cost=d_cost.data_ptr(), want_summary=True)
-        else:
-            s = ctx.generate_check_dev(d_bc.data_ptr(), n, n, MIN_T, flags=flags, index_base=lo,
-                                       d_verdict=d_verdict.data_ptr(), d_first=d_first.data_ptr(),
-                                       d_cost=d_cost.data_ptr(), want_summary=True)
-        return exchange(s)
-
-    def exchange(s):
-        """The one exchange step: all-gather of the per-shard summary records over NCCL, merged on every rank."""
-        return sharding.exchange_summaries(s, dev, gather_buf)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # ---- device-resident timing ---------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        summary = step_device()
-    barrier()
-    launches0 = ctx.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier()
-        ev0.record(stream)
-        pairs_total = 0
-        for _ in range(args.steps):
-            summary = step_device()
-            pairs_total += summary["pairs_checked"]
-        ev1.record(stream)
-        barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = pairs_total / (ms * 1e-3)
-    clocks = clk.summary()
-
-    # ---- end to end: pinned host buffers through the host-pointer C-ABI call --------------------------------
-    e2e = None
-    if not args.no_e2e:
-        # the whole shard when it is at most 2^22 candidates (c3: all 2^20); a 2^22 prefix of it otherwise (c5)
-        ne = min(n, 1 << 22)
-        if name in ("c1", "c2"):
-            bc_host = torch.from_numpy(np.ascontiguousarray(bc_h[:, :ne])).pin_memory()
-            sph_host = torch.from_numpy(np.ascontiguousarray(sph_h[:, :ne])).pin_memory() if sph_h is not None else None
-        else:
-            bc_host = torch.empty((abi.BC_ROWS, ne), dtype=torch.float64).pin_memory()
-            bc_host.copy_(d_bc[:, :ne])
-            sph_host = None
-        v_host = torch.empty(ne, dtype=torch.uint8).pin_memory()
-        f_host = torch.empty(ne, dtype=torch.int32).pin_memory()
-        c_host = torch.empty(ne, dtype=torch.float64).pin_memory()
-        import ctypes as C
-        summ = abi.Summary()
-        lib = ctx.lib
-
-        def step_host():
-            inp = abi.BcSoa(bc_host.data_ptr(), ne, abi.GOAL_ALL, 0)
-            if name == "c1":
-                out = abi.Out(verdict=v_host.data_ptr(), cost=c_host.data_ptr(), summary=C.pointer(summ))
-                st = lib.rqcd_generate_check_pairwise(ctx.h, C.byref(inp), sph_host.data_ptr(), ne, ne, MIN_T, 0, lo, C.byref(out))
-            else:
-                out = abi.Out(verdict=v_host.data_ptr(), first_obstacle=f_host.data_ptr(), cost=c_host.data_ptr(),
-                              summary=C.pointer(summ))
-                st = lib.rqcd_generate_check(ctx.h, C.byref(inp), ne, MIN_T, flags, lo, C.byref(out))
-            assert st == abi.OK, st
-            return exchange(summ.as_dict())
-
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(3):
-            step_host()
-        barrier()
-        ev0.record(stream)
-        e_pairs = 0
-        for _ in range(e2e_steps):
-            e_pairs += step_host()["pairs_checked"]
-        ev1.record(stream)
-        barrier()
-        e_ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms = float(t.item())
-        h2d = 19 * ne * 8 + (4 * ne * 8 if name == "c1" else 0)
-        d2h = ne * (1 + 8) + (0 if name == "c1" else 4 * ne) + 88
-        e2e = {"value": e_pairs / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": e_ms / e2e_steps, "steps": e2e_steps, "candidates_per_rank_per_step": ne}
+    t = res.time_steps(args.steps, args.warmup)
+    ms, value, summary = t["ms"], t["value"], t["summary"]
+    e2e = None if args.no_e2e else res.time_e2e(max(3, min(args.steps, 10)))
 
     # ---- rank 0: CPU baseline on a bounded sample, flop model, roofline ---------------------------------------
+    line = None
     if rank == 0:
         from oracle import binding as B
         orc = B.Oracle()
         n_s = max(1024, min(n, (1 << 22) // max(pairs_per_traj, 1)))
-        bc_s, sph_s = host_inputs(name, W, lo, n_s)
+        bc_s, sph_s = host_inputs(name, W, res.lo, n_s)
         if name == "c1":
             o = orc.generate_check_pairwise(bc_s, sph_s, MIN_T, nthreads=os.cpu_count() or 1, stats=True)
         else:
-            o = orc.generate_check(bc_s, obs, m, MIN_T, flags=flags, matrix=False, nthreads=os.cpu_count() or 1, stats=True)
+            o = orc.generate_check(bc_s, res.obs, m, MIN_T, flags=res.flags, matrix=False, nthreads=os.cpu_count() or 1, stats=True)
         fpc = flops_per_check(o["stats"], pairs_per_traj)
         # parity spot check of the resident results against the oracle sample (the checker, not the product)
-        got = d_verdict[:n_s].cpu().numpy()
+        got = res.d_verdict[:n_s].cpu().numpy()
         parity = int((got != o["verdict"]).sum())
 
         cpu_baseline = None
@@ -413,15 +543,15 @@ def main():
             impl, kind = cpu_checker()
             threads = os.cpu_count() or 1
             n_c = max(1024, min(n, (1 << 25) // max(pairs_per_traj, 1)))  # ~1 s on 16 threads = ~16 core-seconds
-            bc_c, sph_c = host_inputs(name, W, lo, n_c)
-            run_cpu(impl, name, obs, m, bc_c[:, :1024].copy(), None if sph_c is None else sph_c[:, :1024].copy(), threads)
-            r, dt = run_cpu(impl, name, obs, m, bc_c, sph_c, threads)
+            bc_c, sph_c = host_inputs(name, W, res.lo, n_c)
+            run_cpu(impl, name, res.obs, m, bc_c[:, :1024].copy(), None if sph_c is None else sph_c[:, :1024].copy(), threads)
+            r, dt = run_cpu(impl, name, res.obs, m, bc_c, sph_c, threads)
             cpu_baseline = {"value": r["summary"]["pairs_checked"] / dt, "unit": UNIT, "cores": threads, "kind": kind,
                             "sample": f"first {n_c} candidates of rank 0's shard x {pairs_per_traj} obstacles, {dt:.2f} s wall"}
 
-        peaks = ctx.measure_fp64_peak(200)
-        kernel_s = (ms * 1e-3) / args.steps  # k_check dominates the step (k_finalize + memset ~ microseconds)
-        pairs_per_launch = pairs_total / args.steps / world
+        peaks = rig.ctx.measure_fp64_peak(200)
+        kernel_s = (ms * 1e-3) / args.steps  # the check kernel dominates the step (k_finalize, memset, exchange ~ microseconds)
+        pairs_per_launch = t["pairs_total"] / args.steps / world
         achieved = fpc * pairs_per_launch / kernel_s / 1e12
         peak_tf = peaks["dmul_dadd_flops"] / 1e12
         measured = {}
@@ -430,18 +560,16 @@ def main():
         except Exception:
             pass
         bytes_per_launch = n * (19 * 8 + 1 + 4 + 8)
-        traffic = None
-        try:  # DRAM bytes of one launch from the committed ncu capture of this workload (not measured in this run)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[name]["dram_bytes_per_launch"]
-        except Exception:
-            pass
+        traffic, traffic_src = traffic_for(t["kernel"], name)
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-            "traffic": traffic,
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": t["kernel"],
             "peak_source": "measured in this run by rqcd_measure_fp64_peak: dependent-free DMUL+DADD chains (the "
                            "ceiling of the -fmad=false exact mode); dfma_peak is the FMA-counted figure",
             "dfma_peak": peaks["dfma_flops"] / 1e12, "frac_of_dfma_peak": achieved / (peaks["dfma_flops"] / 1e12),
-            "flops_per_check": fpc, "kernel_ms": kernel_s * 1e3,
+            "flops_per_check": fpc, "flops_per_check_meaning": "ALGORITHMIC: the reference's operation count for these pairs "
+            "(SURVEY 8(d) formula fed by the oracle's work counters); the kernel executes fewer (certified solver skip, far cull)",
+            "kernel_ms": kernel_s * 1e3,
             "hbm": {"achieved_gbs": bytes_per_launch / kernel_s / 1e9, "peak_gbs": measured.get("hbm_gbs"),
                     "algorithmic_bytes_per_launch": bytes_per_launch},
         }
@@ -449,19 +577,26 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{name}: {w['desc']}", "candidates_per_rank": n, "candidates_total": n_global,
+            "config": {"workload": f"{name}: {w['desc']}", "candidates_per_rank": n, "candidates_total": res.n_global,
                        "obstacles": pairs_per_traj, "min_time_section": MIN_T, "mode": "exact (no FMA contraction)",
                        "l2": "inputs (19 x n doubles per rank) exceed the 126 MB L2" if 19 * n * 8 > 126e6 else
                              "inputs fit in L2; the kernel is FP64-bound (0.16 KB per candidate), no flush",
-                       "parallelism": f"candidate-index shards x{world}, obstacle set replicated"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                       "parallelism": f"candidate-index shards x{world}, obstacle set replicated",
+                       "exchange": "in-library: ncclAllGather of the 88-byte summaries + merge kernel on the compute stream, "
+                                   "no host sync inside the timed region" if world > 1 else "single shard (merge kernel only)"},
+            "clocks": t["clocks"], "e2e": e2e, "gpu_launches": t["launches"], "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "trajectories_per_sec": t["trajectories_per_sec"],
             "summary": summary, "parity_mismatches_vs_oracle_sample": parity, "oracle_sample": n_s,
         }
+    del res
+    rig.torch.cuda.empty_cache()
+    if not args.no_extras and name != "c5":
+        blk = c5_block(rig, 3)
+        if line is not None:
+            line["c5"] = blk
+    if line is not None:
         emit(line)
-    ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    rig.close()
 
 
 if __name__ == "__main__":

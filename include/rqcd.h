@@ -157,7 +157,13 @@ typedef struct rqcd_out {
   int64_t coeff_stride;
   rqcd_summary* summary;   /* HOST pointer (also with RQCD_F_DEVICE_PTRS); may be NULL. When non-NULL
                               the call synchronises the context's stream before returning. */
+  uint8_t* fragile;        /* [n], with RQCD_F_FRAGILE (required then): 1 when the trajectory's verdict or first obstacle
+                              may depend on the last bits of the cubic solver's acos / cos / pow, see the flag */
+  double* params;          /* rqcd_generate only: RQCD_PARAM_ROWS rows alpha x,y,z, beta x,y,z, gamma x,y,z =
+                              GetAxisParamAlpha/Beta/Gamma(axis) (RapidTrajectoryGenerator.hpp:219-229); may be NULL */
+  int64_t param_stride;
 } rqcd_out;
+#define RQCD_PARAM_ROWS 9
 
 /* flags */
 #define RQCD_F_DEVICE_PTRS 0x1u /* every data pointer in the in/out structs is a device pointer on the
@@ -168,6 +174,26 @@ typedef struct rqcd_out {
  * completely before the launch. */
 #define RQCD_F_EARLY_EXIT 0x2u  /* stop each trajectory at its first non-NoCollision obstacle (what the
                                    Forest driver does); default is all pairs */
+
+/* Diagnostic: mark the results that are NOT pinned by the reference's arithmetic. Every operation of the path is the
+ * reference's own IEEE sequence except the transcendental core of Quartic::solveP3 (src/quartic.cpp:50-55, :60: acos, cos,
+ * pow), where the reference calls its C library and this library evaluates polynomials (<= 1.5 ulp); glibc itself gives
+ * different last bits on different CPUs. Where the closed-form roots are ill-conditioned (grazing contact, coefficient
+ * ratios of 1e3 and more) that ulp decides on which side of the tangent plane a computed critical point lands. With this
+ * flag a second kernel (k_fragile) walks every pair's recursion again, in lockstep with eight copies whose transcendental
+ * outputs are moved by +-2^-50 (the reference's three independent cosines in all sign patterns, Cardano's cube root
+ * relatively), and asks of every SIGN decision of every section -- window vs minTimeSection, midpoint inside, the solver's
+ * branches, each root against ts / mid / tf, the plane side of each test point -- whether it is farther from zero than
+ * 4 x what the perturbation did to it + 8 ulps of the terms it is computed from (its own rounding noise; a plane-side
+ * value on its noise floor is the signature of grazing contact). Decisions that cannot involve the transcendentals (the
+ * first section's window / inside / end-point tests) are exempt. out->fragile[i] = 1 when a pair of trajectory i at or
+ * before its first hit has such a decision; with a verdict_matrix, bit 7 of an entry marks the pair (the verdict stays in
+ * bits 0..1). Verdicts are never changed. An unmarked verdict is the reference's on every conforming libm (tests: every
+ * difference from the CPU reference on adversarial grazing populations is marked, with zero tolerance); a marked one
+ * is a coin toss in the reference too. Monte Carlo batches: ~5e-6 of the pairs. Cost: about the time of the check again
+ * per 2e8 pairs (one thread per pair, compiler divisions). Tunables, read at rqcd_create: RQCD_FRAGILE_LOG2 (magnitudes,
+ * default -50), RQCD_FRAGILE_MARGIN (4), RQCD_FRAGILE_FLOOR (8 ulps). rqcd_fragile_reasons says which decision it was. */
+#define RQCD_F_FRAGILE 0x4u
 
 #define RQCD_MAX_DEPTH 40       /* interval-stack entries per check */
 
@@ -192,6 +218,12 @@ uint64_t rqcd_launch_count(const rqcd_ctx* ctx);
 /* Name of the check kernel of the most recent rqcd_generate_check / rqcd_check / rqcd_generate_check_pairwise /
  * rqcd_plan_best launch on this context ("" before the first): what a profile of the call must show. */
 const char* rqcd_last_kernel_name(const rqcd_ctx* ctx);
+/* RQCD_F_FRAGILE diagnostics: how many pairs this context has marked so far, by the FIRST decision of the pair's recursion
+ * that was not pinned: 0 window vs minTimeSection, 1 midpoint inside, 2 quartic or cubic, 3..10 the solver's branches
+ * (trig / Cardano, |x2| < eps, choice of the resolvent root x2, |D| < eps x2, the two quadratics' discriminants),
+ * 11 + 4 i + {0, 1, 2, 3}: sorted root i against ts / mid / tf and its plane side, 27 / 28 plane side of ts / tf,
+ * 31 the perturbed copies disagreed on the section's result or root count. */
+int rqcd_fragile_reasons(rqcd_ctx* ctx, uint64_t counts[32]);
 
 /* Replaces constructing Sphere / RectPrism objects and the vector<shared_ptr<ConvexObj>> the drivers
  * hold (ForestPerformanceEval.cpp:130-150). Host pointer always. Rotation matrices and half sides are
@@ -203,7 +235,7 @@ int32_t rqcd_num_obstacles(const rqcd_ctx* ctx);
 /* ---- the hot path --------------------------------------------------------- */
 
 /* Generate + GetCost + GetTrajectory only (RapidTrajectoryGenerator.cpp:67-72, .hpp:214-241).
- * Uses out->cost, out->coeffs; other fields ignored. */
+ * Uses out->cost, out->coeffs, out->params; other fields ignored. */
 int rqcd_generate(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, uint32_t flags, rqcd_out* out);
 
 /* Fused Generate -> GetTrajectory -> CollisionCheck against the whole obstacle set: the body of the
@@ -290,6 +322,15 @@ int rqcd_plan_best(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const rqcd_p
  * roots: 3 or 4 rows of n doubles (row stride n); count[n]. Host or device pointers per flags. */
 int rqcd_solve_cubic(rqcd_ctx* ctx, const double* coef, int64_t n, uint32_t flags, double* roots, int32_t* count);
 int rqcd_solve_quartic(rqcd_ctx* ctx, const double* coef, int64_t n, uint32_t flags, double* roots, int32_t* count);
+/* How much each problem's answer depends on the last bits of the solver's acos / cos / pow -- the only operations of the
+ * path that are not the reference's own IEEE sequence (see RQCD_F_FRAGILE). degree 3 or 4, coef as above.
+ * cond[n]: the largest movement of any reported root when those outputs move by eta = 2^-50, divided by eta -- two
+ * conforming math libraries (<= 2 ulp apart) give roots within about cond * 2^-51 of each other, whatever that is
+ * relative to the root (the closed forms lose up to half of the digits on nearly repeated roots).
+ * branch_fragile[n]: 1 when a branch of the solver (three or one real root of the resolvent reported, which resolvent
+ * root, |D| < eps, the sign of a discriminant) is within that movement of its threshold: the COUNT is then libm's choice. */
+int rqcd_solve_conditioning(rqcd_ctx* ctx, int32_t degree, const double* coef, int64_t n, uint32_t flags, double* cond,
+                            uint8_t* branch_fragile);
 
 /* ---- multi-GPU ---------------------------------------------------------------
  * Candidates are sharded by index into contiguous ranges, one per GPU; each GPU holds the full obstacle set. The only

@@ -3,9 +3,10 @@
 //   CommonMath::Vec3 / Rotation / Boundary / ConvexObj / Sphere / RectPrism / Trajectory   (data holders)
 //   RapidQuadrocopterTrajectoryGenerator::RapidTrajectoryGenerator
 //        ctor(x0, v0, a0, gravity), SetGoal{Position,Velocity,Acceleration}[InAxis], Reset, Generate, GetCost,
-//        GetTrajectory                    (reference: include/RapidQuadcopterTrajectories/RapidTrajectoryGenerator.hpp:77-114, 214-241)
+//        GetTrajectory, GetAxisParamAlpha/Beta/Gamma, GetFinalTime, CheckInputFeasibility, CheckPositionFeasibility
+//                                         (reference: include/RapidQuadcopterTrajectories/RapidTrajectoryGenerator.hpp:63-241)
 //   RapidCollisionChecker::CollisionChecker
-//        ctor(Trajectory), CollisionCheck(shared_ptr<ConvexObj>, minTimeSection) -> CollisionResult
+//        ctor(Trajectory), CollisionCheck(Boundary), CollisionCheck(shared_ptr<ConvexObj>, minTimeSection)
 //                                         (reference: include/RapidCollisionDetection/CollisionChecker.hpp:33-61)
 //   rqcd::Batch -- the batched form both drivers' trial loops collapse to (PerformanceEval.cpp:140-182,
 //                  ForestPerformanceEval.cpp:177-225): N candidates x M obstacles in one call.
@@ -55,8 +56,15 @@ class Context {
     if (st == RQCD_OK || (allow_depth_cap && st == RQCD_ERR_DEPTH_CAP)) return;
     throw Error(st, rqcd_last_error(ctx_));
   }
-  // The context single-object facade calls run on (created on first use, device 0 or $RQCD_DEVICE).
+  // The context Batch users may share (created on first use, device 0 or $RQCD_DEVICE).
   static Context& Default() {
+    static Context c(getenv("RQCD_DEVICE") ? atoi(getenv("RQCD_DEVICE")) : 0);
+    return c;
+  }
+  // The context of the single-object calls (RapidTrajectoryGenerator::Generate, CollisionChecker::CollisionCheck, ...):
+  // private to them, because CollisionCheck(obstacle, minT) uploads a one-entry obstacle table for every call and must
+  // not replace the table a Batch on the shared context holds.
+  static Context& Single() {
     static Context c(getenv("RQCD_DEVICE") ? atoi(getenv("RQCD_DEVICE")) : 0);
     return c;
   }
@@ -75,6 +83,10 @@ struct Vec3 {
   Vec3(double xi, double yi, double zi) : x(xi), y(yi), z(zi) {}
   double operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
   double& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
+  Vec3 operator-(const Vec3& r) const { return Vec3(x - r.x, y - r.y, z - r.z); }  // Vec3.hpp:126-128
+  Vec3 operator/(double d) const { return Vec3(x / d, y / d, z / d); }            // Vec3.hpp:164-166
+  double GetNorm2Squared() const { return x * x + y * y + z * z; }                 // Vec3.hpp:103-109 (Dot: x*x + y*y + z*z)
+  double GetNorm2() const { return std::sqrt(GetNorm2Squared()); }                 // Vec3.hpp:112-114
 };
 
 // Unit quaternion (w, x, y, z), local -> global, as Rotation(a, b, c, d) of the reference (Rotation.hpp:42-47).
@@ -86,6 +98,13 @@ struct Rotation {
     const double s = std::sin(angle * 0.5);
     return Rotation(std::cos(angle * 0.5), s * unitAxis.x, s * unitAxis.y, s * unitAxis.z);
   }
+  // direction = axis, magnitude = angle [rad]; below one arc second: identity (Rotation.hpp:82-87)
+  static Rotation FromRotationVector(const Vec3& rotVec) {
+    const double theta = rotVec.GetNorm2();
+    if (theta < 4.84813681e-6) return Identity();
+    return FromAxisAngle(rotVec / theta, theta);
+  }
+  Rotation Inverse() const { return Rotation(v[0], -v[1], -v[2], -v[3]); }  // Rotation.hpp:63-65
 };
 
 struct Boundary {  // ConvexObj.hpp:29-53
@@ -157,6 +176,16 @@ class Trajectory {
   Vec3 operator[](int i) const { return c_[i]; }
   double GetStartTime() const { return t0_; }
   double GetEndTime() const { return t1_; }
+  // The relative position of two trajectories on their common window (Trajectory.hpp:121-128): coefficient-wise
+  // difference, max of the start times, min of the end times. Data arithmetic only -- the check of the result against
+  // a shape is CollisionChecker's; for MANY moving obstacles use MovingObj in a Batch, where the device forms the
+  // difference per (trajectory, obstacle) pair.
+  Trajectory operator-(const Trajectory rhs) const {
+    const double startTime = t0_ < rhs.t0_ ? rhs.t0_ : t0_;  // std::max(_startTime, rhs.GetStartTime())
+    const double endTime = rhs.t1_ < t1_ ? rhs.t1_ : t1_;    // std::min(_endTime, rhs.GetEndTime())
+    return Trajectory(c_[0] - rhs.c_[0], c_[1] - rhs.c_[1], c_[2] - rhs.c_[2], c_[3] - rhs.c_[3], c_[4] - rhs.c_[4],
+                      c_[5] - rhs.c_[5], startTime, endTime);
+  }
 
  private:
   Vec3 c_[6];
@@ -326,6 +355,15 @@ namespace RapidQuadrocopterTrajectoryGenerator {
 
 class RapidTrajectoryGenerator {
  public:
+  enum InputFeasibilityResult {  // RapidTrajectoryGenerator.hpp:63-69 = rqcd_input_feasibility
+    InputFeasible = 0,
+    InputIndeterminable = 1,
+    InputInfeasibleThrustHigh = 2,
+    InputInfeasibleThrustLow = 3,
+    InputInfeasibleRates = 4,
+  };
+  enum StateFeasibilityResult { StateFeasible = 0, StateInfeasible = 1 };  // :71-74
+
   RapidTrajectoryGenerator(const CommonMath::Vec3 x0, const CommonMath::Vec3 v0, const CommonMath::Vec3 a0,
                            const CommonMath::Vec3 gravity)
       : grav_(gravity) {
@@ -338,12 +376,16 @@ class RapidTrajectoryGenerator {
   void SetGoalPositionInAxis(const unsigned ax, const double in) { mask_ |= RQCD_GOAL_POS(ax), bc_[RQCD_BC_PF + ax] = in; }
   void SetGoalVelocityInAxis(const unsigned ax, const double in) { mask_ |= RQCD_GOAL_VEL(ax), bc_[RQCD_BC_VF + ax] = in; }
   void SetGoalAccelerationInAxis(const unsigned ax, const double in) { mask_ |= RQCD_GOAL_ACC(ax), bc_[RQCD_BC_AF + ax] = in; }
-  //! Clears the end-state constraints (goal flags persist across Generate calls, as in the reference).
+  //! Clears the end-state constraints (goal flags persist across Generate calls, as in the reference) and the
+  //! acceleration peak-time cache of CheckInputFeasibility (SingleAxisTrajectory::Reset, SingleAxisTrajectory.cpp:41).
   void Reset() {
     mask_ = 0;
     for (int i = RQCD_BC_PF; i < RQCD_BC_TF; i++) bc_[i] = 0;
+    bc_[RQCD_BC_TF] = 0;
     cost_ = std::numeric_limits<double>::quiet_NaN();
     for (double& c : coeffs_) c = std::numeric_limits<double>::quiet_NaN();
+    for (double& c : abg_) c = std::numeric_limits<double>::quiet_NaN();
+    feasHistory_.clear();
   }
   //! One rqcd_generate launch with n = 1.
   void Generate(const double timeToGo) {
@@ -353,10 +395,17 @@ class RapidTrajectoryGenerator {
     out.cost = &cost_;
     out.coeffs = coeffs_;
     out.coeff_stride = 1;
-    rqcd::Context& c = rqcd::Context::Default();
+    out.params = abg_;
+    out.param_stride = 1;
+    rqcd::Context& c = rqcd::Context::Single();
     c.check(rqcd_generate(c.get(), &in, 1, 0, &out));
   }
   double GetCost() const { return cost_; }
+  double GetFinalTime() const { return bc_[RQCD_BC_TF]; }
+  //! The parameters the generator computed on the device (rqcd_out::params), not back-computed from the coefficients.
+  double GetAxisParamAlpha(int i) const { return abg_[0 + i]; }
+  double GetAxisParamBeta(int i) const { return abg_[3 + i]; }
+  double GetAxisParamGamma(int i) const { return abg_[6 + i]; }
   CommonMath::Trajectory GetTrajectory() const {
     using CommonMath::Vec3;
     const double* k = coeffs_;
@@ -364,14 +413,59 @@ class RapidTrajectoryGenerator {
                                   Vec3(k[9], k[10], k[11]), Vec3(k[12], k[13], k[14]), Vec3(k[15], k[16], k[17]), 0,
                                   bc_[RQCD_BC_TF]);
   }
-  // alpha, beta, gamma follow from the coefficients the GPU returned (c5 = alpha/120, c4 = beta/24, c3 = gamma/6)
-  // only up to rounding, so they are not offered; use GetTrajectory().
+
+  //! rqcd_check_input_feasibility for this object (RapidTrajectoryGenerator.cpp:74-160). The reference caches each
+  //! axis' acceleration peak times in the object from the first call that needed them until Reset()
+  //! (SingleAxisTrajectory.cpp:133-158), so a loop that re-Generates on ONE object evaluates later candidates with the
+  //! first one's peak times (ForestPerformanceEval.cpp:177-209). Reproduced here through the library's `group`
+  //! argument: the object remembers the boundary conditions of every call since Reset() and submits them as one group;
+  //! the answer is the last member's. (A loop over many candidates is what rqcd::Batch::InputFeasibility is for.)
+  InputFeasibilityResult CheckInputFeasibility(double fminAllowed, double fmaxAllowed, double wmaxAllowed,
+                                               double minTimeSection) {
+    feasHistory_.insert(feasHistory_.end(), bc_, bc_ + RQCD_BC_ROWS);
+    const int64_t k = (int64_t)(feasHistory_.size() / RQCD_BC_ROWS);
+    std::vector<double> soa((size_t)RQCD_BC_ROWS * k);
+    for (int64_t j = 0; j < k; j++)
+      for (int r = 0; r < RQCD_BC_ROWS; r++) soa[(size_t)r * k + j] = feasHistory_[(size_t)j * RQCD_BC_ROWS + r];
+    std::vector<int64_t> group(k, 0);
+    std::vector<uint8_t> res(k);
+    rqcd_bc_soa in = {soa.data(), k, mask_, 0};
+    const double g[3] = {grav_.x, grav_.y, grav_.z};
+    rqcd::Context& c = rqcd::Context::Single();
+    c.check(rqcd_check_input_feasibility(c.get(), &in, k, g, fminAllowed, fmaxAllowed, wmaxAllowed, minTimeSection,
+                                         group.data(), 0, res.data()));
+    return (InputFeasibilityResult)res[k - 1];
+  }
+
+  //! rqcd_generate_check_planes with one plane (RapidTrajectoryGenerator.cpp:162-212, the same test as
+  //! CollisionChecker::CollisionCheck(Boundary)): StateInfeasible when the trajectory reaches the plane's wrong side.
+  StateFeasibilityResult CheckPositionFeasibility(CommonMath::Vec3 boundaryPoint, CommonMath::Vec3 boundaryNormal) {
+    const double plane[6] = {boundaryPoint.x, boundaryPoint.y, boundaryPoint.z, boundaryNormal.x, boundaryNormal.y, boundaryNormal.z};
+    rqcd_bc_soa in = {bc_, 1, mask_, 0};
+    uint8_t hit = 0;
+    rqcd::Context& c = rqcd::Context::Single();
+    c.check(rqcd_generate_check_planes(c.get(), &in, 1, plane, 1, 0, &hit, nullptr));
+    return hit ? StateInfeasible : StateFeasible;
+  }
+
+  static const char* GetInputFeasibilityResultName(InputFeasibilityResult fr) {  // :243-257
+    switch (fr) {
+      case InputFeasible: return "Feasible";
+      case InputIndeterminable: return "Indeterminable";
+      case InputInfeasibleThrustHigh: return "InfeasibleThrustHigh";
+      case InputInfeasibleThrustLow: return "InfeasibleThrustLow";
+      case InputInfeasibleRates: return "InfeasibleRates";
+    }
+    return "Unknown!";
+  }
 
  private:
   double bc_[RQCD_BC_ROWS] = {0};
   uint32_t mask_ = 0;
   double cost_;
   double coeffs_[RQCD_COEFF_ROWS];
+  double abg_[RQCD_PARAM_ROWS];
+  std::vector<double> feasHistory_;  // RQCD_BC_ROWS doubles per CheckInputFeasibility call since Reset()
   CommonMath::Vec3 grav_;
 };
 
@@ -385,9 +479,26 @@ class CollisionChecker {
 
   explicit CollisionChecker(CommonMath::Trajectory traj) : traj_(traj) {}
 
-  //! One rqcd_set_obstacles + rqcd_check launch with n = 1, m = 1 on the default context.
+  //! One rqcd_check_planes launch with n = 1, p = 1 (CollisionChecker.hpp:49, src/CollisionChecker.cpp:25-68; see rqcd.h
+  //! for what "crosses the plane" means where the reference's own code reads uninitialised roots).
+  CollisionResult CollisionCheck(CommonMath::Boundary boundary) {
+    const double plane[6] = {boundary.point.x,  boundary.point.y,  boundary.point.z,
+                             boundary.normal.x, boundary.normal.y, boundary.normal.z};
+    double k[RQCD_COEFF_ROWS];
+    for (int i = 0; i < 6; i++)
+      for (int d = 0; d < 3; d++) k[3 * i + d] = traj_[i][d];
+    const double t0 = traj_.GetStartTime(), t1 = traj_.GetEndTime();
+    rqcd_coeff_soa in = {k, 1, &t0, &t1};
+    uint8_t hit = 0;
+    rqcd::Context& c = rqcd::Context::Single();
+    c.check(rqcd_check_planes(c.get(), &in, 1, plane, 1, 0, &hit, nullptr));
+    return hit ? Collision : NoCollision;
+  }
+
+  //! One rqcd_set_obstacles + rqcd_check launch with n = 1, m = 1 on the single-object context (never the context a
+  //! Batch holds its obstacle table on).
   CollisionResult CollisionCheck(std::shared_ptr<CommonMath::ConvexObj> obstacle, double minTimeSection) {
-    rqcd::Context& c = rqcd::Context::Default();
+    rqcd::Context& c = rqcd::Context::Single();
     rqcd_obstacle rec = obstacle->Record();
     c.check(rqcd_set_obstacles(c.get(), &rec, 1));
     double k[RQCD_COEFF_ROWS];

@@ -338,6 +338,15 @@ static int check_section(const double* coef, double ts, double tf, const prep_ob
     st->root_pairs += si.pairs;
   }
   sort_small(roots, rootCount); /* :123 */
+#ifdef ORC_TRACE /* debugging builds only (tools/oracle_perturbed) */
+  if (orc_trace_on) {
+    fprintf(stderr, "depth %d [%.17g, %.17g] mid %.17g n %d roots", depth, ts, tf, midTime, rootCount);
+    for (int i = 0; i < rootCount; i++)
+      fprintf(stderr, " %.17g (D %.3g)", roots[i], v3_dot(v3_sub(traj_value(coef, roots[i]), pp), pn));
+    fprintf(stderr, " | D(ts) %.3g D(tf) %.3g trig %d\n", v3_dot(v3_sub(traj_value(coef, ts), pp), pn),
+            v3_dot(v3_sub(traj_value(coef, tf), pp), pn), si.trig);
+  }
+#endif
 
   double lo[6], hi[6];
   int nlo = 0, nhi = 0;

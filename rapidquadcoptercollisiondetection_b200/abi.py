@@ -20,9 +20,11 @@ NO_COLLISION, COLLISION, INDETERMINABLE, DEPTH_CAP = range(4)
 SPHERE, RECT_PRISM = 0, 1
 BC_P0, BC_V0, BC_A0, BC_PF, BC_VF, BC_AF, BC_TF, BC_ROWS = 0, 3, 6, 9, 12, 15, 18, 19
 COEFF_ROWS = 18
+PARAM_ROWS = 9
 GOAL_ALL = 0x1FF
 F_DEVICE_PTRS = 0x1
 F_EARLY_EXIT = 0x2
+F_FRAGILE = 0x4
 MAX_DEPTH = 40
 COMM_ID_BYTES = 128
 
@@ -105,6 +107,9 @@ class Out(C.Structure):
         ("coeffs", C.c_void_p),
         ("coeff_stride", C.c_int64),
         ("summary", C.POINTER(Summary)),
+        ("fragile", C.c_void_p),
+        ("params", C.c_void_p),
+        ("param_stride", C.c_int64),
     ]
 
 
@@ -122,6 +127,7 @@ SYMBOLS = {
     "rqcd_read_summary": (C.c_int, [_VP, C.POINTER(Summary)]),
     "rqcd_launch_count": (C.c_uint64, [_VP]),
     "rqcd_last_kernel_name": (C.c_char_p, [_VP]),
+    "rqcd_fragile_reasons": (C.c_int, [_VP, _VP]),
     "rqcd_set_obstacles": (C.c_int, [_VP, C.POINTER(Obstacle), C.c_int32]),
     "rqcd_num_obstacles": (C.c_int32, [_VP]),
     "rqcd_generate": (C.c_int, [_VP, C.POINTER(BcSoa), C.c_int64, C.c_uint32, C.POINTER(Out)]),
@@ -141,6 +147,7 @@ SYMBOLS = {
                                  C.POINTER(Summary)]),
     "rqcd_solve_cubic": (C.c_int, [_VP, _VP, C.c_int64, C.c_uint32, _VP, _VP]),
     "rqcd_solve_quartic": (C.c_int, [_VP, _VP, C.c_int64, C.c_uint32, _VP, _VP]),
+    "rqcd_solve_conditioning": (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, C.c_uint32, _VP, _VP]),
     "rqcd_merge_summaries": (C.c_int, [C.POINTER(Summary), C.c_int32, C.POINTER(Summary)]),
     "rqcd_shard_range": (None, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "rqcd_group_create": (C.c_int, [C.POINTER(_VP), C.POINTER(C.c_int32), C.c_int32]),

@@ -109,6 +109,12 @@ class Context:
     def last_kernel_name(self) -> str:
         return (self.lib.rqcd_last_kernel_name(self.h) or b"").decode()
 
+    def fragile_reasons(self):
+        """rqcd_fragile_reasons: marked pairs of this context by the first decision that was not pinned (32 counters)."""
+        out = np.zeros(32, dtype=np.uint64)
+        self._chk(self.lib.rqcd_fragile_reasons(self.h, _ptr(out)))
+        return out
+
     def read_summary(self) -> dict:
         s = abi.Summary()
         self._chk(self.lib.rqcd_read_summary(self.h, C.byref(s)), allow=(abi.ERR_DEPTH_CAP,))
@@ -131,13 +137,23 @@ class Context:
             n = bc.shape[1] - first
         cost = np.empty(n)
         coeffs = np.empty((abi.COEFF_ROWS, n))
-        out = abi.Out(cost=_ptr(cost), coeffs=_ptr(coeffs), coeff_stride=n)
+        params = np.empty((abi.PARAM_ROWS, n))
+        out = abi.Out(cost=_ptr(cost), coeffs=_ptr(coeffs), coeff_stride=n, params=_ptr(params), param_stride=n)
         inp = bc_soa(bc, n, goal_mask, shared_rows, group_size, first)
         self._chk(self.lib.rqcd_generate(self.h, C.byref(inp), n, 0, C.byref(out)))
-        return {"cost": cost, "coeffs": coeffs}
+        return {"cost": cost, "coeffs": coeffs, "abg": params}
 
-    def _host_out(self, n, m, matrix, coeffs, first=True):
+    @staticmethod
+    def _split_fragile(res):
+        """RQCD_F_FRAGILE: bit 7 of a matrix entry marks a fragile pair; hand it out as its own array."""
+        if "verdict_matrix" in res:
+            res["fragile_matrix"] = (res["verdict_matrix"] >> 7).astype(np.uint8)
+            res["verdict_matrix"] &= 0x7F
+
+    def _host_out(self, n, m, matrix, coeffs, first=True, fragile=False):
         res = {"verdict": np.full(n, 255, dtype=np.uint8)}
+        if fragile:
+            res["fragile"] = np.full(n, 255, dtype=np.uint8)
         if first:
             res["first_obstacle"] = np.full(n, -2, dtype=np.int32)
         if coeffs:
@@ -148,26 +164,31 @@ class Context:
         summ = abi.Summary()
         out = abi.Out(verdict=_ptr(res["verdict"]), first_obstacle=_ptr(res.get("first_obstacle")),
                       verdict_matrix=_ptr(res.get("verdict_matrix")), cost=_ptr(res.get("cost")),
-                      coeffs=_ptr(res.get("coeffs")), coeff_stride=n, summary=C.pointer(summ))
+                      coeffs=_ptr(res.get("coeffs")), coeff_stride=n, summary=C.pointer(summ),
+                      fragile=_ptr(res.get("fragile")))
         return res, out, summ
 
     def generate_check(self, bc, min_t, goal_mask=abi.GOAL_ALL, flags=0, index_base=0, matrix=True, n=None, shared_rows=0,
-                       group_size=0, first=0):
+                       group_size=0, first=0, fragile=False):
         """bc: (19, stride) array. With shared_rows (bit mask or row numbers) pass n explicitly: the shared rows hold one
         value per group of group_size candidates, the per-candidate rows n values from element `first`."""
         bc = np.ascontiguousarray(bc, dtype=np.float64)
         if n is None:
             n = bc.shape[1] - first
         m = self.num_obstacles()
-        res, out, summ = self._host_out(n, m, matrix and not (flags & abi.F_EARLY_EXIT), True)
+        if fragile:
+            flags |= abi.F_FRAGILE
+        res, out, summ = self._host_out(n, m, matrix and not (flags & abi.F_EARLY_EXIT), True, fragile=fragile)
         inp = bc_soa(bc, n, goal_mask, shared_rows, group_size, first)
         st = self._chk(self.lib.rqcd_generate_check(self.h, C.byref(inp), n, min_t, flags, index_base, C.byref(out)),
                        allow=(abi.ERR_DEPTH_CAP,))
+        if fragile:
+            self._split_fragile(res)
         res["summary"] = summ.as_dict()
         res["status"] = st
         return res
 
-    def check(self, coeffs, t_end, min_t, t_start=None, cost=None, flags=0, index_base=0, matrix=True):
+    def check(self, coeffs, t_end, min_t, t_start=None, cost=None, flags=0, index_base=0, matrix=True, fragile=False):
         coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
         n = coeffs.shape[1]
         m = self.num_obstacles()
@@ -176,21 +197,26 @@ class Context:
             t_start = np.ascontiguousarray(t_start, dtype=np.float64)
         if cost is not None:
             cost = np.ascontiguousarray(cost, dtype=np.float64)
-        res, out, summ = self._host_out(n, m, matrix and not (flags & abi.F_EARLY_EXIT), False)
+        if fragile:
+            flags |= abi.F_FRAGILE
+        res, out, summ = self._host_out(n, m, matrix and not (flags & abi.F_EARLY_EXIT), False, fragile=fragile)
         inp = abi.CoeffSoa(_ptr(coeffs), n, _ptr(t_start), _ptr(t_end))
         st = self._chk(self.lib.rqcd_check(self.h, C.byref(inp), _ptr(cost), n, min_t, flags, index_base, C.byref(out)),
                        allow=(abi.ERR_DEPTH_CAP,))
+        if fragile:
+            self._split_fragile(res)
         res["summary"] = summ.as_dict()
         res["status"] = st
         return res
 
-    def generate_check_pairwise(self, bc, spheres, min_t, goal_mask=abi.GOAL_ALL, index_base=0):
+    def generate_check_pairwise(self, bc, spheres, min_t, goal_mask=abi.GOAL_ALL, index_base=0, fragile=False):
         bc = np.ascontiguousarray(bc, dtype=np.float64)
         spheres = np.ascontiguousarray(spheres, dtype=np.float64)
         n = bc.shape[1]
-        res, out, summ = self._host_out(n, 1, False, True, first=False)
+        res, out, summ = self._host_out(n, 1, False, True, first=False, fragile=fragile)
         inp = abi.BcSoa(_ptr(bc), n, goal_mask, 0)
-        st = self._chk(self.lib.rqcd_generate_check_pairwise(self.h, C.byref(inp), _ptr(spheres), n, n, min_t, 0,
+        st = self._chk(self.lib.rqcd_generate_check_pairwise(self.h, C.byref(inp), _ptr(spheres), n, n, min_t,
+                                                             abi.F_FRAGILE if fragile else 0,
                                                              index_base, C.byref(out)), allow=(abi.ERR_DEPTH_CAP,))
         res["summary"] = summ.as_dict()
         res["status"] = st
@@ -272,6 +298,15 @@ class Context:
         cnt = np.zeros(n, dtype=np.int32)
         self._chk(self.lib.rqcd_solve_quartic(self.h, _ptr(coef), n, 0, _ptr(roots), _ptr(cnt)))
         return roots, cnt
+
+    def solve_conditioning(self, coef):
+        """rqcd_solve_conditioning: (cond, branch_fragile) per problem; coef has 3 (cubic) or 4 (quartic) rows."""
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        degree, n = coef.shape
+        cond = np.zeros(n)
+        flag = np.zeros(n, dtype=np.uint8)
+        self._chk(self.lib.rqcd_solve_conditioning(self.h, degree, _ptr(coef), n, 0, _ptr(cond), _ptr(flag)))
+        return cond, flag
 
     # ---- device-mode calls (raw device pointers; asynchronous on the context's stream) ----
     def synth_bc(self, seed, index_base, n, d_bc: int, stride: int):

@@ -300,6 +300,7 @@ int validate_out(const rqcd_out* out, uint32_t flags, long long n) {
   if (!out) return RQCD_ERR_INVALID_ARG;
   if ((flags & RQCD_F_EARLY_EXIT) && out->verdict_matrix) return RQCD_ERR_INVALID_ARG;
   if (out->coeffs && out->coeff_stride < n) return RQCD_ERR_INVALID_ARG;
+  if ((flags & RQCD_F_FRAGILE) && !out->fragile) return RQCD_ERR_INVALID_ARG;
   return RQCD_OK;
 }
 
@@ -380,11 +381,31 @@ int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long lo
   return RQCD_OK;
 }
 
+// RQCD_F_FRAGILE: after the base launch, k_fragile walks every pair's recursion in lockstep with four copies whose
+// transcendental outputs (the cubic's cos / sin pair, Cardano's cube root) are moved by +-eta, once per probe magnitude
+// (RQCD_FRAGILE_LOG2, default 2^-50 and 2^-46: ~8 and ~130 ulp, where two conforming math libraries differ by one or
+// two). A pair whose copies do not take the same decisions in every section is marked (see k_fragile).
+int run_fragile_probes(rqcd_ctx* ctx, CheckCall& cc, const OutStage& o, long long n, uint8_t* d_fragile) {
+  RQCD_CU(cudaMemsetAsync(d_fragile, 0, (size_t)n, ctx->stream));
+  CheckParams q = cc.p;
+  q.progress = nullptr;  // the input is all there once the base launch has run
+  q.stream_error = nullptr;
+  const bool moving = ctx->any_moving;
+  for (int k = 0; k < ctx->n_probe_mag; k++) {
+    RQCD_CU(launch_fragile(q, cc.mode, moving && !cc.pairwise, cc.pairwise, std::ldexp(1.0, ctx->probe_log2[k]),
+                           ctx->probe_margin, ctx->probe_floor, cc.pairwise ? nullptr : o.first, d_fragile, cc.pairwise ? nullptr : o.matrix, ctx->d_why,
+                           ctx->stream));
+    ctx->launches++;
+  }
+  return RQCD_OK;
+}
+
 // Shared tail of the three check entry points.
 int finish_check(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, uint32_t flags, long long n, int m,
                  bool want_cost_coeffs) {
   OutStage o;
   const bool dev = flags & RQCD_F_DEVICE_PTRS;
+  const bool fragile = (flags & RQCD_F_FRAGILE) != 0;
   if (dev) {
     o.verdict = out->verdict;
     o.first = out->first_obstacle;
@@ -398,13 +419,43 @@ int finish_check(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, uint32_t fla
     int st = stage_outputs(ctx, out, n, m, want_cost_coeffs, o);
     if (st != RQCD_OK) return st;
   }
+  uint8_t* d_fragile = nullptr;
+  if (fragile) {
+    // the probes are compared by verdict and first hit: both exist on the device even if the caller did not ask for them
+    if (!o.verdict) {
+      RQCD_CU(ensure(ctx->s_verdict, (size_t)(n > 0 ? n : 1)));
+      o.verdict = (uint8_t*)ctx->s_verdict.p;
+    }
+    if (!o.first && !cc.pairwise) {
+      RQCD_CU(ensure(ctx->s_first, (size_t)(n > 0 ? n : 1) * 4));
+      o.first = (int*)ctx->s_first.p;
+    }
+    d_fragile = out->fragile;
+    if (!dev) {
+      RQCD_CU(ensure(ctx->s_fragile, (size_t)(n > 0 ? n : 1)));
+      d_fragile = (uint8_t*)ctx->s_fragile.p;
+    }
+  }
   fill_params_out(cc.p, o);
   cc.p.early_exit = (flags & RQCD_F_EARLY_EXIT) ? 1 : 0;
   int st = dev ? run_check(ctx, cc) : run_host_pipeline(ctx, cc, out, n, m, o);
   if (st != RQCD_OK) return st;
-  if (out->summary) return fetch_summary(ctx, out->summary);
+  int sum_st = RQCD_OK;
+  if (out->summary) {
+    sum_st = fetch_summary(ctx, out->summary);
+    if (sum_st != RQCD_OK && sum_st != RQCD_ERR_DEPTH_CAP) return sum_st;
+  }
+  if (fragile && n > 0) {
+    st = run_fragile_probes(ctx, cc, o, n, d_fragile);
+    if (st != RQCD_OK) return st;
+    if (!dev) {
+      RQCD_CU(cudaMemcpyAsync(out->fragile, d_fragile, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+      if (out->verdict_matrix && m > 0)  // again: bit 7 now marks the fragile pairs
+        RQCD_CU(cudaMemcpyAsync(out->verdict_matrix, o.matrix, (size_t)n * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
   if (!dev) RQCD_CU(cudaStreamSynchronize(ctx->stream));
-  return RQCD_OK;
+  return sum_st;
 }
 
 }  // namespace
@@ -435,6 +486,8 @@ int rqcd_create(rqcd_ctx** out, int device) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counter, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_why, 32 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(ctx->d_why, 0, 32 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_summary, sizeof(DevSummary));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_summary, sizeof(DevSummary));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stream, 2 * sizeof(unsigned long long));
@@ -458,6 +511,22 @@ int rqcd_create(rqcd_ctx** out, int device) {
   if (th && atoi(th) >= 1 && atoi(th) <= 32) ctx->th_plane = atoi(th);
   const char* to = getenv("RQCD_STREAM_TIMEOUT_CYCLES");
   if (to && atoll(to) > 0) ctx->stream_timeout = atoll(to);
+  const char* fl = getenv("RQCD_FRAGILE_LOG2");  // magnitudes of the RQCD_F_FRAGILE probes, e.g. "-50,-47,-44"
+  if (fl && *fl) {
+    ctx->n_probe_mag = 0;
+    for (const char* q = fl; *q && ctx->n_probe_mag < 8;) {
+      char* end = nullptr;
+      const long v = strtol(q, &end, 10);
+      if (end == q) break;
+      if (v <= -30 && v >= -60) ctx->probe_log2[ctx->n_probe_mag++] = (int)v;
+      q = (*end == ',') ? end + 1 : end;
+    }
+    if (ctx->n_probe_mag == 0) ctx->n_probe_mag = 1, ctx->probe_log2[0] = -50;
+  }
+  const char* fm = getenv("RQCD_FRAGILE_MARGIN");
+  if (fm && atof(fm) >= 1.0) ctx->probe_margin = atof(fm);
+  const char* ff = getenv("RQCD_FRAGILE_FLOOR");
+  if (ff && atof(ff) >= 0.0) ctx->probe_floor = atof(ff);
   const char* ls = getenv("RQCD_LOCKSTEP");
   if (ls && (ls[0] == '0' || ls[0] == '1') && ls[1] == 0) ctx->lockstep = ls[0] - '0';
   *out = ctx;
@@ -472,9 +541,11 @@ void rqcd_destroy(rqcd_ctx* ctx) {
   if (ctx->d_merged) cudaFree(ctx->d_merged);
   release(ctx->obs_blob);
   DevBuf* bufs[] = {&ctx->s_in,     &ctx->s_aux,   &ctx->s_verdict, &ctx->s_first,  &ctx->s_matrix, &ctx->s_cost,
-                    &ctx->s_coeffs, &ctx->s_roots, &ctx->s_count,   &ctx->s_planes, &ctx->s_peaks,  &ctx->s_group};
+                    &ctx->s_coeffs, &ctx->s_roots, &ctx->s_count,   &ctx->s_planes, &ctx->s_peaks,  &ctx->s_group,
+                    &ctx->s_fragile};
   for (DevBuf* b : bufs) release(*b);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
+  if (ctx->d_why) cudaFree(ctx->d_why);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_summary) cudaFree(ctx->d_summary);
   if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
@@ -538,6 +609,14 @@ int rqcd_read_summary(rqcd_ctx* ctx, rqcd_summary* out) {
 uint64_t rqcd_launch_count(const rqcd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 const char* rqcd_last_kernel_name(const rqcd_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
+
+int rqcd_fragile_reasons(rqcd_ctx* ctx, uint64_t counts[32]) {
+  if (!ctx || !counts) return RQCD_ERR_INVALID_ARG;
+  DeviceGuard g(ctx->device);
+  RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  RQCD_CU(cudaMemcpy(counts, ctx->d_why, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return RQCD_OK;
+}
 
 int rqcd_set_obstacles(rqcd_ctx* ctx, const rqcd_obstacle* obstacles, int32_t m) {
   if (!ctx || m < 0 || (m > 0 && !obstacles)) return RQCD_ERR_INVALID_ARG;
@@ -619,13 +698,14 @@ int32_t rqcd_num_obstacles(const rqcd_ctx* ctx) { return ctx ? ctx->m : -1; }
 int rqcd_generate(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, uint32_t flags, rqcd_out* out) {
   if (!ctx || !out || bad_bc(in, n)) return RQCD_ERR_INVALID_ARG;
   if (out->coeffs && out->coeff_stride < n) return RQCD_ERR_INVALID_ARG;
+  if (out->params && out->param_stride < n) return RQCD_ERR_INVALID_ARG;
   if (n == 0) return RQCD_OK;
   DeviceGuard g(ctx->device);
   CheckParams p = {};
   p.n = n;
   if (flags & RQCD_F_DEVICE_PTRS) {
     bind_bc(p, in);
-    RQCD_CU(launch_generate(p, out->cost, out->coeffs, out->coeff_stride, ctx->stream));
+    RQCD_CU(launch_generate(p, out->cost, out->coeffs, out->coeff_stride, out->params, out->param_stride, ctx->stream));
     ctx->launches++;
     return RQCD_OK;
   }
@@ -643,10 +723,16 @@ int rqcd_generate(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, uint32_t flag
     o.coeffs = (double*)ctx->s_coeffs.p;
     o.coeff_stride = n;
   }
-  RQCD_CU(launch_generate(p, o.cost, o.coeffs, o.coeff_stride, ctx->stream));
+  double* d_params = nullptr;
+  if (out->params) {
+    RQCD_CU(ensure(ctx->s_roots, (size_t)n * 8 * RQCD_PARAM_ROWS));
+    d_params = (double*)ctx->s_roots.p;
+  }
+  RQCD_CU(launch_generate(p, o.cost, o.coeffs, o.coeff_stride, d_params, n, ctx->stream));
   ctx->launches++;
   if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost, o.cost, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (o.coeffs) RQCD_CU(rows_d2h(out->coeffs, out->coeff_stride, o.coeffs, n, RQCD_COEFF_ROWS, ctx->stream));
+  if (d_params) RQCD_CU(rows_d2h(out->params, out->param_stride, d_params, n, RQCD_PARAM_ROWS, ctx->stream));
   RQCD_CU(cudaStreamSynchronize(ctx->stream));
   return RQCD_OK;
 }
@@ -888,7 +974,7 @@ int rqcd_plan_best(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const rqcd_p
   uint8_t* d_stage = (dev && stage) ? stage : d_stage_scratch;
   uint8_t* d_verdict = (uint8_t*)ctx->s_verdict.p;
   // stage 0: Generate + GetCost
-  RQCD_CU(launch_generate(p, d_cost, nullptr, 0, s));
+  RQCD_CU(launch_generate(p, d_cost, nullptr, 0, nullptr, 0, s));
   ctx->launches += n > 0;
   // stage 1: CheckInputFeasibility
   if (prm->check_input && n > 0) {
@@ -963,6 +1049,31 @@ int rqcd_solve_cubic(rqcd_ctx* ctx, const double* coef, int64_t n, uint32_t flag
 }
 int rqcd_solve_quartic(rqcd_ctx* ctx, const double* coef, int64_t n, uint32_t flags, double* roots, int32_t* count) {
   return solve_common(ctx, true, coef, n, flags, roots, count);
+}
+
+int rqcd_solve_conditioning(rqcd_ctx* ctx, int32_t degree, const double* coef, int64_t n, uint32_t flags, double* cond,
+                            uint8_t* branch_fragile) {
+  if (!ctx || n < 0 || (degree != 3 && degree != 4) || (n > 0 && (!coef || !cond || !branch_fragile))) return RQCD_ERR_INVALID_ARG;
+  if (n == 0) return RQCD_OK;
+  DeviceGuard g(ctx->device);
+  const bool quartic = degree == 4;
+  const double eta = std::ldexp(1.0, ctx->probe_log2[0]);
+  if (flags & RQCD_F_DEVICE_PTRS) {
+    RQCD_CU(launch_solve_cond(quartic, coef, n, eta, ctx->probe_margin, ctx->probe_floor, cond, branch_fragile, ctx->stream));
+    ctx->launches++;
+    return RQCD_OK;
+  }
+  RQCD_CU(ensure(ctx->s_in, (size_t)n * 8 * degree));
+  RQCD_CU(ensure(ctx->s_roots, (size_t)n * 8));
+  RQCD_CU(ensure(ctx->s_fragile, (size_t)n));
+  RQCD_CU(cudaMemcpyAsync(ctx->s_in.p, coef, (size_t)n * 8 * degree, cudaMemcpyHostToDevice, ctx->stream));
+  RQCD_CU(launch_solve_cond(quartic, (const double*)ctx->s_in.p, n, eta, ctx->probe_margin, ctx->probe_floor,
+                            (double*)ctx->s_roots.p, (uint8_t*)ctx->s_fragile.p, ctx->stream));
+  ctx->launches++;
+  RQCD_CU(cudaMemcpyAsync(cond, ctx->s_roots.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RQCD_CU(cudaMemcpyAsync(branch_fragile, ctx->s_fragile.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  RQCD_CU(cudaStreamSynchronize(ctx->stream));
+  return RQCD_OK;
 }
 
 int rqcd_merge_summaries(const rqcd_summary* shards, int32_t n_shards, rqcd_summary* merged) {

@@ -34,6 +34,7 @@ struct rqcd_ctx {
   rqcd::DevBuf obs_blob;
   // launch scratch
   unsigned long long* d_counter = nullptr;
+  unsigned long long* d_why = nullptr;  // [32] RQCD_F_FRAGILE: marked pairs by the first decision that was not pinned
   rqcd::BlockPartial* d_partials = nullptr;
   int partial_cap = 0;
   rqcd::DevSummary* d_summary = nullptr;
@@ -48,12 +49,14 @@ struct rqcd_ctx {
   rqcd::DevSummary* d_merged = nullptr;  // merge of the table (rqcd_exchange_summaries)
   bool merged_valid = false;
   // staging for host-pointer calls
-  rqcd::DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group;
+  rqcd::DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group, s_fragile;
   int refill_min = 0;  // RQCD_REFILL_MIN override; 0 = chosen from the obstacle count
   int lockstep = -1;   // RQCD_LOCKSTEP override (0/1); -1 = chosen from the obstacle count
   int pool = 1;        // RQCD_POOL (0/1): k_pool (staged sections, certified solver skip) for obstacle tables
   int th_solve = 32, th_plane = 24;  // RQCD_TH_SOLVE / RQCD_TH_PLANE: see CheckParams
   long long stream_timeout = 1ll << 32;  // RQCD_STREAM_TIMEOUT_CYCLES (~2 s): a streamed chunk that never arrives fails the call
+  int n_probe_mag = 1, probe_log2[8] = {-50, 0, 0, 0, 0, 0, 0, 0};  // RQCD_F_FRAGILE probe magnitudes 2^k (RQCD_FRAGILE_LOG2)
+  double probe_margin = 4.0, probe_floor = 8.0;  // RQCD_FRAGILE_MARGIN, RQCD_FRAGILE_FLOOR (ulps), see k_fragile
   const char* last_kernel = "";  // name of the check kernel of the most recent launch (rqcd_last_kernel_name)
   unsigned long long launches = 0;
   char last_error[512] = {0};

@@ -32,6 +32,7 @@
 // k_check_pool (further down) is the kernel of ONE shape -- all pairs against a static table of 16..100 obstacles
 // -- built around the first frame of a pair: first frames in obstacle order with X(mid) evaluated once per
 // trajectory, the pairs that need a recursion as tasks in a per-warp pool; same frame(), same verdicts.
+#include <cstdio>
 #include "rqcd_kernel_util.cuh"
 
 namespace rqcd {
@@ -470,6 +471,298 @@ __global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int
   }
 }
 
+// ---- RQCD_F_FRAGILE: which results hinge on the last bits of the cubic solver's acos / cos / pow ---------------------
+// Everything on the path is the reference's own IEEE operation sequence except those three calls (glibc there, polynomials
+// here; two conforming libraries differ by an ulp or two). Where the closed-form roots are ill-conditioned -- grazing
+// contact with coefficient ratios of 1e3 and more -- that ulp is amplified until it decides on which side of the tangent
+// plane a computed critical point lands, and the reference's own answer is a coin toss. k_fragile finds those pairs.
+//
+// One thread per (trajectory i, obstacle k) pair, obstacle-major (the lanes of a warp read neighbouring candidates and one
+// obstacle record). The thread walks the pair's recursion (end-point tests in the first section, depth first, low child
+// parked: CollisionChecker.cpp:70-193) NINE times in lockstep: copy 0 as shipped, copies 1..8 with the three cosines of
+// solveP3's trigonometric branch moved by +-eta in all eight sign patterns (the reference takes three independent cos()
+// calls) and Cardano's cube root by the relative factor 1 +- eta. Every copy keeps its own interval ends -- a child
+// interval is bounded by a computed root, so the copies' sections drift apart by what the perturbation did to that root.
+//
+// A section is a list of SIGN DECISIONS (SectionProbe::q): window against minTimeSection, midpoint inside the obstacle,
+// quartic or cubic, the solver's own branches (SolverDecision), every sorted root against ts / mid / tf, the plane side
+// of every root inside the section and of both ends. Each comes with the magnitude of the terms it is the difference of
+// (SectionProbe::s): its own rounding noise is a few ulps of that. The copies act as a numerical derivative of each
+// quantity with respect to the transcendental outputs. A decision is PINNED when
+//     |q(copy 0)| >= margin * max_v |q(copy v) - q(copy 0)| + floor_ulps * 2^-53 * s      (defaults: 4 and 8),
+// i.e. when it is farther from zero than what the perturbation did to it AND than the rounding noise of its own
+// evaluation (a root whose response to eta is below one ulp still moves by that ulp for some libm, and with it a
+// plane-side value that sits on its noise floor -- the signature of grazing contact). Decisions that do not depend on
+// the transcendentals at all -- the first section's window, inside test, degree test and end-point sides, and those of
+// children whose interval ends are exact midpoints -- are exempt: they are the reference's bits. A pair is MARKED at
+// the first section where a needed decision is not pinned (or the copies disagree on the root count or the section's
+// result); unmarked pairs take copy 0's decisions -- the shipped kernels' -- for every libm within eta.
+enum ProbeSlot {
+  PQ_WINDOW = 0,  // (tf - ts) - minT                              (:93-96)
+  PQ_INSIDE,      // sphere: r - |Xm - c|; prism: min_i (h_i - |q_i|)   (:89-92)
+  PQ_QUART,       // |pc[0]| - 1e-6                                (:47, :116)
+  PQ_SOLVER,      // SD_COUNT entries
+  PQ_ROOT = PQ_SOLVER + SD_COUNT,  // per sorted root: r - ts, r - mid, r - tf, plane side (4 x 4)
+  PQ_DTS = PQ_ROOT + 16, PQ_DTF,   // plane side of the section's ends
+  PQ_COUNT
+};
+struct SectionProbe {
+  int sig;         // StepResult | has_hi << 4 | has_lo << 5 | root count << 8
+  unsigned need;   // which q[] entries decide this section
+  double t_next, lo_tf, mid;
+  double q[PQ_COUNT], s[PQ_COUNT];
+};
+// sum_d |n_d| (sum_k |c_kd| |t|^(5-k) + |point_d|): the magnitude of the terms of (X(t) - point) . n
+RQCD_DEV double side_scale(const double (&c)[18], double t, V3 pp, V3 pn) {
+  const double T = fabs(t);
+  double ax = 0.0, ay = 0.0, az = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) ax = ax * T + fabs(c[3 * k]), ay = ay * T + fabs(c[3 * k + 1]), az = az * T + fabs(c[3 * k + 2]);
+  return fabs(pn.x) * (ax + fabs(pp.x)) + fabs(pn.y) * (ay + fabs(pp.y)) + fabs(pn.z) * (az + fabs(pp.z));
+}
+
+// `clean`: the section's ends do not depend on a computed root (the first section; children bounded by midpoints)
+template <class Obs>
+RQCD_DEV void probe_section(const double (&c)[18], double ts, double tf, const EndPoints ends, bool first, bool clean,
+                            const Obs& obs, double minT, const Perturb pt, SectionProbe& o) {
+  const double mid = (ts + tf) / 2;
+  const V3 Xm = traj_value(c, mid);
+  const V3 ctr = obs.center();
+  const double rad = obs.radius();
+  const bool prism = Obs::kSphereOnly ? false : obs.prism();
+  const bool in_ends = first && ends_inside(obs, ends.xs(), ends.xf());
+  __syncwarp();
+  PlainMath pm;
+  pm.pt = pt;
+  pm.pt.diag = true;
+  bool in_m;
+  V3 pp, pn;
+  double pc[5], r[4];
+  const int n = plane_and_roots(pm, c, obs, Xm, ctr, rad, prism, in_m, pp, pn, pc, r[0], r[1], r[2], r[3]);
+  sort_roots(n, r[0], r[1], r[2], r[3]);
+  Children ch;
+  section_children(c, ts, tf, mid, pp, pn, pc, n, r[0], r[1], r[2], r[3], ends.amax(), !in_m, ch);
+  int res = (ch.has_hi | ch.has_lo) ? STEP_CHILD : STEP_CLEAR;
+  if (tf - ts < minT) res = STEP_INDETERM;
+  if (in_m) res = STEP_COLLISION;
+  if (in_ends) res = STEP_COLLISION;
+  o.sig = res | ((res == STEP_CHILD) ? ((ch.has_hi ? 16 : 0) | (ch.has_lo ? 32 : 0)) : 0);
+  o.t_next = ch.t_next, o.lo_tf = ch.lo_tf, o.mid = mid;
+#pragma unroll
+  for (int j = 0; j < PQ_COUNT; j++) o.q[j] = kNoDecision, o.s[j] = 0.0;
+  o.q[PQ_WINDOW] = (tf - ts) - minT;
+  o.s[PQ_WINDOW] = fabs(tf) + fabs(ts);
+  const double xs = ((fabs(Xm.x) + fabs(Xm.y)) + fabs(Xm.z)) + ((fabs(ctr.x) + fabs(ctr.y)) + fabs(ctr.z));
+  if (prism) {
+    const V3 qm = rotate<Obs, true>(obs, Xm - ctr);
+    o.q[PQ_INSIDE] = fmin(fmin(obs.half(0) - fabs(qm.x), obs.half(1) - fabs(qm.y)), obs.half(2) - fabs(qm.z));
+    o.s[PQ_INSIDE] = 2.0 * xs + fmax(fmax(obs.half(0), obs.half(1)), obs.half(2));
+  } else {
+    o.q[PQ_INSIDE] = rad - norm2(Xm - ctr);
+    o.s[PQ_INSIDE] = xs + rad;
+  }
+  unsigned need = 0;
+  if (!in_ends) {  // a first section decided by the end points is the same in every copy
+    if (!clean) need |= 1u << PQ_INSIDE;
+    if (!in_m) {
+      if (!clean) need |= 1u << PQ_WINDOW;
+      if (res != STEP_INDETERM) {
+        const bool quart = fabs(pc[0]) > 1e-6;
+        o.q[PQ_QUART] = fabs(pc[0]) - 1e-6;
+        o.s[PQ_QUART] = 5.0 * ((fabs(pn.x * c[0]) + fabs(pn.y * c[1])) + fabs(pn.z * c[2]));
+        if (!clean) need |= (1u << PQ_QUART) | (1u << (PQ_SOLVER + SD_TRIG));
+        need |= 1u << (PQ_SOLVER + SD_X2);
+        if (quart) need |= (((1u << SD_COUNT) - 1u) & ~(1u << SD_TRIG)) << PQ_SOLVER;
+#pragma unroll
+        for (int j = 0; j < SD_COUNT; j++) o.q[PQ_SOLVER + j] = pm.pt.q[j], o.s[PQ_SOLVER + j] = pm.pt.qs[j];
+        o.sig |= n << 8;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (i < n) {
+            o.q[PQ_ROOT + 4 * i + 0] = r[i] - ts, o.s[PQ_ROOT + 4 * i + 0] = fabs(r[i]) + fabs(ts);
+            o.q[PQ_ROOT + 4 * i + 1] = r[i] - mid, o.s[PQ_ROOT + 4 * i + 1] = fabs(r[i]) + fabs(mid);
+            o.q[PQ_ROOT + 4 * i + 2] = r[i] - tf, o.s[PQ_ROOT + 4 * i + 2] = fabs(r[i]) + fabs(tf);
+            need |= 7u << (PQ_ROOT + 4 * i);  // the caller drops comparisons that cannot matter, see k_fragile
+            o.q[PQ_ROOT + 4 * i + 3] = dot(traj_value(c, r[i]) - pp, pn);  // :157-158, :180-181
+            // + what one ulp of the root does: D'(t) = the velocity polynomial the root was computed from
+            const double t = r[i], dv = fabs((((pc[0] * t + pc[1]) * t + pc[2]) * t + pc[3]) * t + pc[4]);
+            o.s[PQ_ROOT + 4 * i + 3] = side_scale(c, t, pp, pn) + dv * fabs(t);
+            if (r[i] > ts && r[i] < tf) need |= 8u << (PQ_ROOT + 4 * i);
+          }
+        }
+        o.q[PQ_DTS] = dot(traj_value(c, ts) - pp, pn), o.s[PQ_DTS] = side_scale(c, ts, pp, pn);
+        o.q[PQ_DTF] = dot(traj_value(c, tf) - pp, pn), o.s[PQ_DTF] = side_scale(c, tf, pp, pn);
+        if (!clean) need |= (1u << PQ_DTS) | (1u << PQ_DTF);
+      }
+    }
+  }
+  o.need = need;
+}
+
+template <int MODE, bool MOVING, bool PAIRWISE>
+__global__ void __launch_bounds__(128) k_fragile(const CheckParams p, double eta, double margin, double floor_ulps, const int* first,
+                                                 uint8_t* fragile, uint8_t* matrix, unsigned long long* why) {
+  static_assert(PQ_COUNT <= 32, "the need mask is one word");
+  constexpr int kCopies = 9;
+  const int lane = threadIdx.x & 31;
+  const long long m = PAIRWISE ? 1 : p.m, total = p.n * m;
+  const double* tab = reinterpret_cast<const double*>(p.obs_blob);
+  const int* oflags = PAIRWISE ? nullptr : reinterpret_cast<const int*>(tab + (size_t)p.stride * p.mp);
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long j0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x - lane); j0 < total; j0 += step) {
+    const long long j = j0 + lane;
+    bool alive = j < total;
+    const long long i = alive ? j % p.n : 0;
+    const int k = alive ? (int)(j / p.n) : 0;
+    if (alive && p.skip && p.skip[i] != 0) alive = false;
+    // a pair behind the trajectory's first hit cannot change the trajectory's result; it only matters to the matrix
+    const bool counts = !first || first[i] < 0 || k <= first[i];
+    if (!matrix && !counts) alive = false;
+    double c[18], t0 = 0.0, t1 = 0.0, cost;
+#pragma unroll
+    for (int q = 0; q < 18; q++) c[q] = 0.0;
+    if (alive) load_trajectory<MODE>(p, i, c, t0, t1, cost);
+    LaneSphere sph = {0.0, 0.0, 0.0, 1.0};
+    TableObs obs;
+    obs.rec = PAIRWISE ? nullptr : tab + (size_t)k * p.stride;
+    if (PAIRWISE && alive) {
+      sph.cx = ld_in(p.spheres + i), sph.cy = ld_in(p.spheres + p.sphere_stride + i);
+      sph.cz = ld_in(p.spheres + 2 * p.sphere_stride + i), sph.r = ld_in(p.spheres + 3 * p.sphere_stride + i);
+    }
+    if (MOVING && alive && (oflags[k] & OBS_MOVING)) {  // Trajectory::operator- (Trajectory.hpp:121-128)
+#pragma unroll
+      for (int q = 0; q < 18; q++) c[q] = c[q] - obs.rec[OF_MOTION + q];
+      const double ms = obs.rec[OF_MT0], me = obs.rec[OF_MT1];
+      t0 = (t0 < ms) ? ms : t0;
+      t1 = (me < t1) ? me : t1;
+      if (!(t0 <= t1)) alive = false;  // no common window: NoCollision without a section
+    }
+    double endrow[EndPoints::kRows];
+    EndPoints ends;
+    ends.slot = endrow, ends.stride = 1;
+    ends.set_xs(traj_value(c, t0));
+    ends.set_xf(traj_value(c, t1));
+    ends.set_amax(side_filter_bound(c, t0, t1));
+    double ts[kCopies], tf[kCopies];
+    double2 stack[kCopies][kMaxDepth];
+#pragma unroll
+    for (int v = 0; v < kCopies; v++) ts[v] = t0, tf[v] = t1;
+    int sp = 0;
+    unsigned long long dirty_stack = 0;  // bit d: the interval parked at depth d has a root-derived end
+    bool first_frame = true, frag = false, clean = true;
+    while (__any_sync(kFull, alive)) {
+      SectionProbe base;
+      double spread[PQ_COUNT], t_next[kCopies], lo_tf[kCopies];
+      bool differs = false;
+#pragma unroll 1
+      for (int v = 0; v < kCopies; v++) {
+        Perturb pt;
+        pt.on = v != 0;
+        const int bits = v - 1;
+        pt.d[0] = (bits & 1) ? eta : -eta, pt.d[1] = (bits & 2) ? eta : -eta, pt.d[2] = (bits & 4) ? eta : -eta;
+        pt.a = 1.0 + pt.d[0];
+        SectionProbe o;
+        if (PAIRWISE) probe_section(c, ts[v], tf[v], ends, first_frame, clean, sph, p.min_t, pt, o);
+        else probe_section(c, ts[v], tf[v], ends, first_frame, clean, obs, p.min_t, pt, o);
+        if (v == 0) {
+          base = o;
+#pragma unroll
+          for (int q = 0; q < PQ_COUNT; q++) spread[q] = 0.0;
+        } else {
+          differs = differs | (o.sig != base.sig);
+#pragma unroll
+          for (int q = 0; q < PQ_COUNT; q++) {
+            const bool same = __double_as_longlong(o.q[q]) == __double_as_longlong(base.q[q]);
+            const double d = fabs(o.q[q] - base.q[q]);
+            // NaN differences (a NaN on one side only, inf - inf) count as unbounded
+            spread[q] = same ? spread[q] : ((d == d) ? fmax(spread[q], d) : __longlong_as_double(0x7ff0000000000000ll));
+          }
+        }
+        t_next[v] = o.t_next, lo_tf[v] = o.lo_tf;
+      }
+      first_frame = false;
+      if (alive) {
+        int reason = differs ? 31 : -1;  // 31: the copies disagree on the section's result or root count
+        unsigned pinned = 0;
+#pragma unroll
+        for (int q = 0; q < PQ_COUNT; q++) {
+          // a NaN that every copy shares comes from the inputs, not from the transcendentals: every comparison with it is
+          // false on every libm
+          const bool shared_nan = base.q[q] != base.q[q] && spread[q] == 0.0;
+          const bool ok = shared_nan || fabs(base.q[q]) >= margin * spread[q] + floor_ulps * 1.1102230246251565e-16 * base.s[q];
+          pinned |= ok ? (1u << q) : 0u;
+        }
+        // Where a root lies relative to ts / mid / tf only matters if the root can be on the obstacle side, or if the end
+        // it sits next to can (the child spawned by that end is bounded by its neighbour in the list, :166, :183). A root
+        // of a child section often IS the child's start: on a flat face the child's plane is the parent's.
+        unsigned need = base.need;
+        {
+          const bool ts_free = (clean || ((pinned >> PQ_DTS) & 1u)) && base.q[PQ_DTS] > 0.0;
+          const bool tf_free = (clean || ((pinned >> PQ_DTF) & 1u)) && base.q[PQ_DTF] > 0.0;
+#pragma unroll
+          for (int r_ = 0; r_ < 4; r_++) {
+            const int b = PQ_ROOT + 4 * r_;
+            const bool root_free = ((pinned >> (b + 3)) & 1u) && base.q[b + 3] > 0.0;
+            const unsigned drop = ((ts_free ? 1u : 0u) | 2u | (tf_free ? 4u : 0u)) << b;
+            if (root_free) need &= ~drop;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < PQ_COUNT; q++)
+          if (((need >> q) & 1u) && !((pinned >> q) & 1u)) {
+            differs = true;
+            reason = reason < 0 ? q : reason;
+          }
+        const int res = base.sig & 7;
+        if (differs) {
+          frag = true;
+          alive = false;
+          if (why) {
+            const unsigned long long seen = atomicAdd(why + reason, 1ull);
+#ifdef RQCD_FRAGILE_DEBUG
+            if (seen < 3 && reason < PQ_COUNT)
+              printf("fragile i %lld k %d reason %d q %.17g spread %.3g scale %.3g ts %.17g tf %.17g sig %x depth %d clean %d\n", i, k, reason,
+                     base.q[reason], spread[reason], base.s[reason], ts[0], tf[0], base.sig, sp, (int)clean);
+#else
+            (void)seen;
+#endif
+          }
+        } else if (res == STEP_CHILD) {
+          const bool hi = (base.sig & 16) != 0, lo = (base.sig & 32) != 0;
+          if (hi & lo) {
+            if (sp < kMaxDepth) {
+#pragma unroll
+              for (int v = 0; v < kCopies; v++) stack[v][sp] = make_double2(ts[v], lo_tf[v]);
+              const bool lo_clean = clean && __double_as_longlong(base.lo_tf) == __double_as_longlong(base.mid);
+              dirty_stack = (dirty_stack & ~(1ull << sp)) | (lo_clean ? 0ull : (1ull << sp));
+              sp++;
+            } else {
+              alive = false;  // depth cap: reported by the check itself
+            }
+          }
+          clean = clean && __double_as_longlong(base.t_next) == __double_as_longlong(base.mid);
+#pragma unroll
+          for (int v = 0; v < kCopies; v++) {
+            if (hi) ts[v] = t_next[v];
+            else tf[v] = t_next[v];
+          }
+        } else if (res == STEP_CLEAR && sp > 0) {
+          sp--;
+          clean = ((dirty_stack >> sp) & 1ull) == 0;
+#pragma unroll
+          for (int v = 0; v < kCopies; v++) ts[v] = stack[v][sp].x, tf[v] = stack[v][sp].y;
+        } else {
+          alive = false;  // the pair is decided, the same way in every copy
+        }
+      }
+    }
+    if (frag) {
+      if (matrix) matrix[i * m + k] |= 0x80;
+      if (fragile && counts) fragile[i] = 1;
+    }
+  }
+}
+
 // ---- multi-GPU exchange (rqcd_multi_*): a shard's summary goes to its slot of a table on the first device -- a store
 // through peer-mapped memory (NVLink) or zero-copy host memory -- and one thread block there merges the table with
 // rqcd_merge_summaries' rule: counts add; best = lowest cost, lowest index on ties (identical for every shard count).
@@ -501,7 +794,10 @@ __global__ void k_merge_summaries(const DevSummary* slots, int n, DevSummary* ou
 }
 
 // ---- RapidTrajectoryGenerator::Generate + GetCost + GetTrajectory only --------------------------------
-__global__ void __launch_bounds__(256) k_generate(const CheckParams p, double* cost, double* coeffs, long long coeff_stride) {
+// params (may be null): 9 rows alpha xyz, beta xyz, gamma xyz -- GetAxisParamAlpha/Beta/Gamma (.hpp:219-229), the values the
+// generator computed, not back-computed from the coefficients
+__global__ void __launch_bounds__(256) k_generate(const CheckParams p, double* cost, double* coeffs, long long coeff_stride,
+                                                  double* params, long long param_stride) {
   const long long n = p.n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double c[18], t0, t1, co;
@@ -510,6 +806,19 @@ __global__ void __launch_bounds__(256) k_generate(const CheckParams p, double* c
     if (coeffs) {
 #pragma unroll
       for (int j = 0; j < 18; j++) coeffs[j * coeff_stride + i] = c[j];
+    }
+    if (params) {
+      const BcIndex x = bc_index(p, i);
+      const double Tf = bc_at(p, 18, x);
+#pragma unroll
+      for (int ax = 0; ax < 3; ax++) {
+        const AxisParams q = gen_axis(bc_at(p, 0 + ax, x), bc_at(p, 3 + ax, x), bc_at(p, 6 + ax, x), bc_at(p, 9 + ax, x),
+                                      bc_at(p, 12 + ax, x), bc_at(p, 15 + ax, x), (p.goal_mask >> (3 * ax)) & 1,
+                                      (p.goal_mask >> (3 * ax + 1)) & 1, (p.goal_mask >> (3 * ax + 2)) & 1, Tf);
+        params[(0 + ax) * param_stride + i] = q.a;
+        params[(3 + ax) * param_stride + i] = q.b;
+        params[(6 + ax) * param_stride + i] = q.g;
+      }
     }
   }
 }
@@ -793,8 +1102,8 @@ int sm_count() {
   return sms;
 }
 
-int grid_for(long long n, int cap) {
-  long long b = (n + 255) / 256;
+int grid_for(long long n, int cap, int threads = 256) {
+  long long b = (n + threads - 1) / threads;
   if (b < 1) b = 1;
   if (b > cap) b = cap;
   return (int)b;
@@ -863,6 +1172,27 @@ cudaError_t launch_merge_summaries(const DevSummary* slots, int n, DevSummary* o
   return cudaGetLastError();
 }
 
+cudaError_t launch_fragile(const CheckParams& p, int mode, bool moving, bool pairwise, double eta, double margin, double floor_ulps,
+                           const int* first, uint8_t* fragile, uint8_t* matrix, unsigned long long* why, cudaStream_t s) {
+  const long long total = p.n * (long long)(pairwise ? 1 : p.m);
+  if (total <= 0) return cudaSuccess;
+  const int grid = grid_for(total, sm_count() * 16, 128);
+  const bool bc = mode == MODE_BC;
+#define RQCD_FRAGILE(MODE, MOVING, PAIRWISE) k_fragile<MODE, MOVING, PAIRWISE><<<grid, 128, 0, s>>>(p, eta, margin, floor_ulps, first, fragile, matrix, why)
+  if (pairwise) {
+    if (bc) RQCD_FRAGILE(MODE_BC, false, true);
+    else RQCD_FRAGILE(MODE_COEFF, false, true);
+  } else if (moving) {
+    if (bc) RQCD_FRAGILE(MODE_BC, true, false);
+    else RQCD_FRAGILE(MODE_COEFF, true, false);
+  } else {
+    if (bc) RQCD_FRAGILE(MODE_BC, false, false);
+    else RQCD_FRAGILE(MODE_COEFF, false, false);
+  }
+#undef RQCD_FRAGILE
+  return cudaGetLastError();
+}
+
 cudaError_t launch_finalize(const BlockPartial* partials, int grid, DevSummary* d_summary, cudaStream_t s) {
   k_finalize<<<1, 256, 0, s>>>(partials, grid, d_summary);
   return cudaGetLastError();
@@ -905,15 +1235,85 @@ cudaError_t launch_plan_stage(long long n, const uint8_t* verdict, uint8_t* stag
   return cudaGetLastError();
 }
 
-cudaError_t launch_generate(const CheckParams& p, double* cost, double* coeffs, long long coeff_stride, cudaStream_t s) {
+cudaError_t launch_generate(const CheckParams& p, double* cost, double* coeffs, long long coeff_stride, double* params,
+                            long long param_stride, cudaStream_t s) {
   if (p.n <= 0) return cudaSuccess;
-  k_generate<<<grid_for(p.n, sm_count() * 8), 256, 0, s>>>(p, cost, coeffs, coeff_stride);
+  k_generate<<<grid_for(p.n, sm_count() * 8), 256, 0, s>>>(p, cost, coeffs, coeff_stride, params, param_stride);
   return cudaGetLastError();
 }
 
 cudaError_t launch_solve(bool quartic, const double* coef, long long n, double* roots, int* count, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   k_solve<<<grid_for(n, sm_count() * 8), 256, 0, s>>>(quartic, coef, n, roots, count);
+  return cudaGetLastError();
+}
+
+// rqcd_solve_conditioning: the solver of k_solve nine times per problem (see k_fragile): copy 0 as shipped, eight with the
+// transcendental outputs moved by +-eta. cond = the largest movement of any reported root divided by eta: how many units a
+// root moves per unit of libm error. flag = a branch decision of the solver (SolverDecision) is not pinned, or the
+// copies disagree on the root count: the reference's own count is a coin toss there.
+__global__ void __launch_bounds__(128) k_solve_cond(bool quartic, const double* coef, long long n, double eta, double margin,
+                                                    double floor_ulps, double* cond, uint8_t* flag) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += step) {
+    const long long i = i0 + (threadIdx.x & 31);
+    const bool live = i < n;
+    const long long j = live ? i : n - 1;
+    const double a = coef[j], b = coef[n + j], c = coef[2 * n + j], d = quartic ? coef[3 * n + j] : 0.0;
+    double base_r[4] = {0, 0, 0, 0}, base_q[SD_COUNT], base_s[SD_COUNT], spread[SD_COUNT], moved = 0.0;
+    int base_cnt = 0;
+    bool bad = false;
+#pragma unroll 1
+    for (int v = 0; v < 9; v++) {
+      PlainMath pm;
+      pm.pt.on = v != 0;
+      pm.pt.diag = true;
+      const int bits = v - 1;
+      pm.pt.d[0] = (bits & 1) ? eta : -eta, pm.pt.d[1] = (bits & 2) ? eta : -eta, pm.pt.d[2] = (bits & 4) ? eta : -eta;
+      pm.pt.a = 1.0 + pm.pt.d[0];
+      double r[4] = {0, 0, 0, 0};
+      const int cnt = quartic ? solve_quartic(pm, a, b, c, d, r[0], r[1], r[2], r[3]) : solve_p3(pm, a, b, c, r[0], r[1], r[2]);
+      const int used = quartic ? cnt : 3;  // the cubic reports Re / Im of the complex pair in x[1], x[2]
+      if (v == 0) {
+        base_cnt = cnt;
+#pragma unroll
+        for (int q = 0; q < 4; q++) base_r[q] = r[q];
+#pragma unroll
+        for (int q = 0; q < SD_COUNT; q++) base_q[q] = pm.pt.q[q], base_s[q] = pm.pt.qs[q], spread[q] = 0.0;
+      } else {
+        bad = bad | (cnt != base_cnt);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (q < used && cnt == base_cnt && __double_as_longlong(r[q]) != __double_as_longlong(base_r[q])) {
+            const double dr = fabs(r[q] - base_r[q]);
+            moved = (dr == dr) ? fmax(moved, dr) : __longlong_as_double(0x7ff0000000000000ll);
+          }
+#pragma unroll
+        for (int q = 0; q < SD_COUNT; q++)
+          if (__double_as_longlong(pm.pt.q[q]) != __double_as_longlong(base_q[q])) {
+            const double dq = fabs(pm.pt.q[q] - base_q[q]);
+            spread[q] = (dq == dq) ? fmax(spread[q], dq) : __longlong_as_double(0x7ff0000000000000ll);
+          }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < SD_COUNT; q++) {
+      if (q == SD_TRIG) continue;  // decided before any transcendental: the reference's own bits
+      if (!quartic && q != SD_X2) continue;
+      const bool shared_nan = base_q[q] != base_q[q] && spread[q] == 0.0;
+      if (!shared_nan && !(fabs(base_q[q]) >= margin * spread[q] + floor_ulps * 1.1102230246251565e-16 * base_s[q])) bad = true;
+    }
+    if (live) {
+      cond[i] = moved / eta;
+      flag[i] = bad ? 1 : 0;
+    }
+  }
+}
+
+cudaError_t launch_solve_cond(bool quartic, const double* coef, long long n, double eta, double margin, double floor_ulps,
+                              double* cond, uint8_t* flag, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_solve_cond<<<grid_for(n, sm_count() * 16, 128), 128, 0, s>>>(quartic, coef, n, eta, margin, floor_ulps, cond, flag);
   return cudaGetLastError();
 }
 

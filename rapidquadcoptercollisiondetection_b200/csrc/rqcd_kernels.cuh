@@ -90,6 +90,13 @@ cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t sm
 const char* check_kernel_name(bool moving, bool pairwise, int m);
 constexpr int kEndBitsMinObstacles = 16;  // static tables at least this long: end-point tests as a pre-pass
 cudaError_t launch_finalize(const BlockPartial* partials, int grid, DevSummary* d_summary, cudaStream_t s);
+// RQCD_F_FRAGILE (k_fragile): every pair's recursion once more, in lockstep with eight copies whose cubic-solver
+// transcendentals are moved by +-eta; a pair with a sign decision that is not `margin` times farther from zero than the
+// copies scatter is marked: bit 7 of matrix[i*m + k], and fragile[i] when the pair is at or before the trajectory's
+// first hit first[i] (null: every pair counts). Null arrays are skipped.
+cudaError_t launch_fragile(const CheckParams& p, int mode, bool moving, bool pairwise, double eta, double margin, double floor_ulps,
+                           const int* first, uint8_t* fragile, uint8_t* matrix, unsigned long long* why /* [32] or null */,
+                           cudaStream_t s);
 // multi-GPU exchange (rqcd_multi.cu): a shard's summary to its slot of a table (peer-mapped memory of the group's first
 // device, or the all-gather's receive buffer); the merge of all slots into *out (and *copy when given)
 cudaError_t launch_publish_summary(const DevSummary* mine, DevSummary* slot, cudaStream_t s);
@@ -112,8 +119,11 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
 cudaError_t launch_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas, const uint8_t* plane_hit,
                              uint8_t* stage, cudaStream_t s);
 cudaError_t launch_plan_stage(long long n, const uint8_t* verdict, uint8_t* stage, cudaStream_t s);
-cudaError_t launch_generate(const CheckParams& p, double* cost, double* coeffs, long long coeff_stride, cudaStream_t s);
+cudaError_t launch_generate(const CheckParams& p, double* cost, double* coeffs, long long coeff_stride, double* params,
+                            long long param_stride, cudaStream_t s);
 cudaError_t launch_solve(bool quartic, const double* coef, long long n, double* roots, int* count, cudaStream_t s);
+cudaError_t launch_solve_cond(bool quartic, const double* coef, long long n, double eta, double margin, double floor_ulps,
+                              double* cond, uint8_t* flag, cudaStream_t s);
 cudaError_t launch_synth_bc(unsigned long long seed, long long index_base, long long n, double* bc, long long stride,
                             cudaStream_t s);
 cudaError_t launch_fp64_peak(bool fma, int blocks, int iters, double* sink, cudaStream_t s);

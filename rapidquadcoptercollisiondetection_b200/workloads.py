@@ -25,9 +25,14 @@ def _splitmix64(x: np.ndarray) -> np.ndarray:
 def synth_bc(seed: int, index_base: int, n: int) -> np.ndarray:
     """19 x n boundary conditions, identical to rqcd_synth_bc / orc_synth_bc.
     Ranges of test/PerformanceEval.cpp:59-65: pos0 = 0, vel0/acc0/posf/velf/accf U(-4,4), Tf U(0.2,4)."""
+    return synth_bc_at(seed, np.arange(index_base, index_base + n, dtype=np.uint64))
+
+
+def synth_bc_at(seed: int, indices) -> np.ndarray:
+    """synth_bc for an arbitrary list of global candidate indices (e.g. every 1024-th of a shard)."""
     with np.errstate(over="ignore"):
-        g = np.arange(index_base, index_base + n, dtype=np.uint64)
-        bc = np.empty((abi.BC_ROWS, n))
+        g = np.asarray(indices).astype(np.uint64)
+        bc = np.empty((abi.BC_ROWS, len(g)))
         for r in range(abi.BC_ROWS):
             k = _splitmix64(np.array([np.uint64(seed) ^ (np.uint64(r) * np.uint64(0xD6E8FEB86659FD93))], dtype=np.uint64))
             h = _splitmix64(k + g)

@@ -76,6 +76,8 @@ def test_goal_flag_combinations(ctx, vectors):
         g = ctx.generate(bc, int(mask))
         assert_close(g["cost"], vectors[f"gm_cost_{j}"], what=f"cost mask {int(mask):#x}")
         assert_close(g["coeffs"], vectors[f"gm_coeffs_{j}"], what=f"coeffs mask {int(mask):#x}")
+        # GetAxisParamAlpha/Beta/Gamma of the unmodified reference (rqcd_out::params)
+        assert_close(g["abg"], vectors[f"gm_abg_{j}"], what=f"alpha/beta/gamma mask {int(mask):#x}")
 
 
 def test_moving_obstacles_match_reference_vectors(ctx, vectors):
@@ -98,12 +100,16 @@ def test_prebuilt_quintics_with_windows(ctx, vectors):
 
 
 def test_solver_vectors(ctx, vectors):
+    """The reference's own solver outputs (tests/golden). Cubic entry 7 is x^3 + 1e6 x^2 + x + 1: r^2 - q^3 cancels
+    catastrophically, the imaginary part the reference reports (4e-10, true value 1e-3) is rounding noise of ITS pow()
+    and decides `fabs(x[2]) < eps` -- rqcd_solve_conditioning must say so (branch-fragile), not a skip list."""
     roots, cnt = ctx.solve_quartic(vectors["sq_coef"])
-    assert_roots_match(vectors["sq_coef"], roots, cnt, vectors["sq_roots"], vectors["sq_count"], "quartic")
+    cond, fr = ctx.solve_conditioning(vectors["sq_coef"])
+    print("quartic vectors:", assert_roots_match(vectors["sq_coef"], roots, cnt, vectors["sq_roots"], vectors["sq_count"], cond, fr, "quartic"))
     roots, cnt = ctx.solve_cubic(vectors["sc_coef"])
-    # entry 7 is x^3 + 1e6 x^2 + x + 1: r^2 - q^3 cancels catastrophically, the imaginary part the reference
-    # reports (4e-10, true value 1e-3) is rounding noise of ITS pow() and decides `fabs(x[2]) < eps`
-    assert_roots_match(vectors["sc_coef"], roots, cnt, vectors["sc_roots"], vectors["sc_count"], "cubic", skip=(7,))
+    cond, fr = ctx.solve_conditioning(vectors["sc_coef"])
+    print("cubic vectors:", assert_roots_match(vectors["sc_coef"], roots, cnt, vectors["sc_roots"], vectors["sc_count"], cond, fr, "cubic"))
+    assert fr[7] == 1
 
 
 def test_solver_random_against_oracle(ctx, oracle):
@@ -111,11 +117,17 @@ def test_solver_random_against_oracle(ctx, oracle):
     q = np.concatenate([rng.uniform(-10, 10, (4, 200_000)), rng.normal(0, 100, (4, 50_000))], axis=1)
     ra, ca = ctx.solve_quartic(q)
     rb, cb = oracle.solve_quartic(q)
-    assert_roots_match(q, ra, ca, rb, cb, "quartic")
+    cond, fr = ctx.solve_conditioning(q)
+    st = assert_roots_match(q, ra, ca, rb, cb, cond, fr, "quartic")
+    print("quartic random:", st)
+    assert st["branch_fragile"] <= 1e-3 * st["problems"]  # the flag is specific
     c = rng.uniform(-10, 10, (3, 200_000))
     ra, ca = ctx.solve_cubic(c)
     rb, cb = oracle.solve_cubic(c)
-    assert_roots_match(c, ra, ca, rb, cb, "cubic")
+    cond, fr = ctx.solve_conditioning(c)
+    st = assert_roots_match(c, ra, ca, rb, cb, cond, fr, "cubic")
+    print("cubic random:", st)
+    assert st["branch_fragile"] <= 1e-3 * st["problems"]
 
 
 @pytest.mark.parametrize("n,ns,npz,seed", [(20_000, 32, 32, 101), (50_000, 5, 0, 102), (3_000, 0, 40, 103), (777, 1, 0, 104)])
@@ -305,6 +317,45 @@ def test_degenerate_inputs_follow_the_reference_arithmetic(ctx, oracle):
     assert set(np.unique(o["verdict_matrix"])) == {0, 1, 2}
 
 
+def test_fragile_mark_is_rare_on_monte_carlo(ctx, oracle):
+    """RQCD_F_FRAGILE on the Monte Carlo shapes (static table, moving table, early exit, pairwise): verdicts equal the
+    oracle's on every pair, the marks change nothing, and fewer than 1e-4 of the pairs are marked."""
+    specs = W.static_obstacles(2, 32, 32)
+    obs = abi.make_obstacles(specs)
+    bc = W.synth_bc(1, 0, 1 << 15)
+    ctx.set_obstacles(obs, len(specs))
+    r = ctx.generate_check(bc, MIN_T, fragile=True)
+    o = oracle.generate_check(bc, obs, len(specs), MIN_T, nthreads=8)
+    np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"])
+    np.testing.assert_array_equal(r["verdict"], o["verdict"])
+    assert (r["fragile_matrix"] != 0).mean() < 1e-4
+    assert r["fragile"].max() <= 1
+    e = ctx.generate_check(bc, MIN_T, flags=abi.F_EARLY_EXIT, fragile=True)
+    oe = oracle.generate_check(bc, obs, len(specs), MIN_T, flags=abi.F_EARLY_EXIT, matrix=False, nthreads=8)
+    np.testing.assert_array_equal(e["verdict"], oe["verdict"])
+    np.testing.assert_array_equal(e["first_obstacle"], oe["first_obstacle"])
+    assert e["fragile"].mean() < 1e-3
+    # a trajectory marked in early-exit mode is marked in all-pairs mode too (same pairs up to the first hit)
+    assert not ((e["fragile"] != 0) & (r["fragile"] == 0)).any()
+    mspecs = W.moving_obstacles(4, 16, lambda b: ctx.generate(b)["coeffs"])
+    mobs = abi.make_obstacles(mspecs)
+    ctx.set_obstacles(mobs, len(mspecs))
+    rm = ctx.generate_check(bc[:, :8192], MIN_T, fragile=True)
+    om = oracle.generate_check(bc[:, :8192], mobs, len(mspecs), MIN_T, nthreads=8)
+    np.testing.assert_array_equal(rm["verdict_matrix"], om["verdict_matrix"])
+    assert (rm["fragile_matrix"] != 0).mean() < 1e-3
+    u = W.synth_bc(8, 0, 1 << 15)
+    sph = np.empty((4, 1 << 15))
+    sph[0:3] = u[3:6]
+    sph[3] = 0.1 + (u[6] + 4.0) / 8.0 * 1.4
+    rp = ctx.generate_check_pairwise(bc, sph, MIN_T, fragile=True)
+    op = oracle.generate_check_pairwise(bc, sph, MIN_T, nthreads=8)
+    np.testing.assert_array_equal(rp["verdict"], op["verdict"])
+    assert rp["fragile"].mean() < 1e-3
+    print("fragile marks: static", int((r["fragile_matrix"] != 0).sum()), "early-exit trajectories", int(e["fragile"].sum()),
+          "moving", int((rm["fragile_matrix"] != 0).sum()), "pairwise", int(rp["fragile"].sum()), "reasons", ctx.fragile_reasons().tolist())
+
+
 def test_grazing_and_badly_scaled_trajectories(ctx, oracle):
     """The two places where the kernel leaves its fast forms and must land on the reference's literal arithmetic:
     (1) plane-side tests whose value is within the certified margin of zero -- trajectories that graze an obstacle's
@@ -313,8 +364,11 @@ def test_grazing_and_badly_scaled_trajectories(ctx, oracle):
     1e+60, 1e+100) redo the frame section with the compiler's IEEE operators. Verdicts must equal the oracle's.
     With coefficient ratios of 1e3..1e8 the reference's own closed-form roots are off by more than the grazing
     distance, and a last-bit difference in acos / cos / pow (glibc there, polynomials here) moves the computed
-    critical point across the plane: those pairs are the documented limit of verdict parity and
-    are only bounded here (0.14 % of this population; the same 561 pairs for every kernel build of this round)."""
+    critical point across the plane. Those pairs are not tolerated by a quota: RQCD_F_FRAGILE marks the pairs in whose
+    recursion some sign decision is closer to zero than the cubic's transcendental outputs (moved by 2^-50) and the
+    decision's own rounding noise can move it, and EVERY pair that differs from the oracle must carry the mark, at every
+    ratio -- outside the marked set verdicts are bit-exact. (On Monte Carlo batches the mark is rare:
+    test_fragile_mark_is_rare_on_monte_carlo.)"""
     coeffs, t_end, specs = grazing_case(log_a=(1.0, 2.0))
     obs = abi.make_obstacles(specs)
     ctx.set_obstacles(obs, len(specs))  # 20 obstacles: end-point pre-pass kernel
@@ -326,11 +380,24 @@ def test_grazing_and_badly_scaled_trajectories(ctx, oracle):
     r = ctx.check(coeffs, t_end, MIN_T)
     np.testing.assert_array_equal(r["verdict_matrix"], o["verdict_matrix"][:, :3])
 
-    coeffs, t_end, specs = grazing_case(log_a=(1.0, 8.0))
-    ctx.set_obstacles(obs, len(specs))
-    r = ctx.check(coeffs, t_end, MIN_T)
-    o = oracle.check(coeffs, t_end, obs, len(specs), MIN_T, nthreads=8)
-    assert int((r["verdict_matrix"] != o["verdict_matrix"]).sum()) <= 0.005 * o["verdict_matrix"].size
+    for log_a in ((1.0, 2.0), (1.0, 4.0), (3.0, 6.0), (1.0, 8.0), (6.0, 8.0)):
+        coeffs, t_end, specs = grazing_case(log_a=log_a)
+        ctx.set_obstacles(obs, len(specs))
+        r = ctx.check(coeffs, t_end, MIN_T, fragile=True)
+        plain = ctx.check(coeffs, t_end, MIN_T)
+        np.testing.assert_array_equal(r["verdict_matrix"], plain["verdict_matrix"])  # the marks change no verdict
+        o = oracle.check(coeffs, t_end, obs, len(specs), MIN_T, nthreads=8)
+        differs = r["verdict_matrix"] != o["verdict_matrix"]
+        marked = r["fragile_matrix"] != 0
+        print(f"grazing log_a={log_a}: {int(differs.sum())} pairs differ, {int(marked.sum())} of {marked.size} marked fragile")
+        assert not (differs & ~marked).any(), f"{int((differs & ~marked).sum())} unmarked mismatches at log_a={log_a}"
+        # the three near obstacles of this population graze by construction (within 1e-13 .. 1e-6 of the surface with
+        # coefficients up to 1e8: below the rounding noise of the reference's own plane-side evaluation for most of them);
+        # the 17 far spheres are crossed at speeds up to 1e8 and are rarely marked
+        assert marked[:, :3].mean() < 0.75 and marked[:, 3:].mean() < 0.01
+        # per trajectory: a differing verdict / first hit implies the trajectory's mark
+        t_differs = (r["verdict"] != o["verdict"]) | (r["first_obstacle"] != o["first_obstacle"])
+        assert not (t_differs & (r["fragile"] == 0)).any()
 
     # badly scaled scenes: the same random scene multiplied by a power of ten (positions, sizes and coefficients)
     base = W.synth_bc(88, 0, 4096)

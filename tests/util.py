@@ -35,46 +35,50 @@ def _polyval_monic(coef, x):
     return y
 
 
-def assert_roots_match(coef, roots_a, cnt_a, roots_b, cnt_b, what="", skip=()):
-    """(a = CUDA path, b = reference/oracle.)  Bar: root counts equal and roots within 1e-9 relative.
+def assert_roots_match(coef, roots_a, cnt_a, roots_b, cnt_b, cond, fragile, what=""):
+    """(a = CUDA path, b = reference/oracle.)  No quota: every problem is held to a bound of its own.
 
-    The closed-form solver of src/quartic.cpp is ill-conditioned on a thin set of inputs (a nearly repeated
-    root of the resolvent's h-quadratic, `D = y*y - 4*d` ~ 1e-7 y*y; a knife-edge `fabs(x[2]) < eps` or
-    `D < 0`): there a last-ulp difference in acos/cos/pow -- which no device libm shares with glibc -- moves
-    the REFERENCE's own roots by up to ~1e-7 relative (its error against the true roots is that large too)
-    or changes its root count. Those cases may be at most 1e-4 of a random batch, must agree to 1e-5, and
-    the CUDA root must be no worse a root of the polynomial than the reference's (residual test)."""
+    Everything in src/quartic.cpp is IEEE arithmetic the CUDA path repeats operation by operation, except acos / cos /
+    pow(x, 1/3), where glibc and the device polynomials differ by an ulp or two. rqcd_solve_conditioning measures what
+    that ulp is worth per problem: `cond` = root movement per unit of libm error, `fragile` = a branch of the solver
+    (root count!) sits within that movement of its threshold. So
+      * root counts must be equal wherever the problem is not branch-fragile;
+      * every root must agree within 1e-9 relative (the bar of BASELINE.json) OR within cond * 2^-49 absolute -- eight
+        ulps of libm difference amplified by the problem's own conditioning;
+      * on branch-fragile problems with equal counts the CUDA root must still be as good a root of the polynomial as the
+        reference's (residual test)."""
     n = cnt_a.shape[0]
-    keep = np.ones(n, dtype=bool)
-    keep[list(skip)] = False
-    diff = np.flatnonzero((cnt_a != cnt_b) & keep)
-    assert diff.size <= 1e-4 * n, (f"{what}: root counts differ at {diff[:8]}: {cnt_a[diff[:8]]} vs {cnt_b[diff[:8]]}; "
-                                   f"coef {coef[:, diff[:4]].T.tolist()} roots {roots_a[:, diff[:4]].T.tolist()} vs "
-                                   f"{roots_b[:, diff[:4]].T.tolist()}")
-    keep &= cnt_a == cnt_b
+    fragile = np.asarray(fragile) != 0
+    diff = np.flatnonzero((cnt_a != cnt_b) & ~fragile)
+    assert diff.size == 0, (f"{what}: root counts differ on problems that are not branch-fragile, at {diff[:8]}: "
+                            f"{cnt_a[diff[:8]]} vs {cnt_b[diff[:8]]}; coef {coef[:, diff[:4]].T.tolist()}")
+    keep = cnt_a == cnt_b
     rows = roots_a.shape[0]
-    outliers = 0
     with np.errstate(invalid="ignore", over="ignore"):
         scale = np.maximum(1.0, np.nanmax(np.abs(np.where(np.isfinite(coef), coef, 0.0)), axis=0))
+        allow = np.where(np.isfinite(cond), cond, np.inf) * 2.0 ** -49
         for k in range(rows):
             a, b = roots_a[k], roots_b[k]
             live = (cnt_a > k) if rows == 4 else np.ones(n, dtype=bool)  # cubic: x[1], x[2] hold Re/Im when 1 root
             live &= keep
             both_nan = np.isnan(a) & np.isnan(b)
             same_inf = np.isinf(a) & (a == b)
-            err = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), scale)
-            ok = both_nan | same_inf | (err <= REL_TOL) | ~live
-            bad = np.flatnonzero(~ok)
-            outliers += bad.size
-            if bad.size:
-                assert np.all(err[bad] <= 1e-5), f"{what}: root {k} differs at {bad[:5]}: {a[bad[:5]]} vs {b[bad[:5]]}"
-                if rows == 4 or k == 0:  # real roots: ours must be as good a root as the reference's
-                    res_a = np.abs(_polyval_monic(coef[:, bad], a[bad]))
-                    res_b = np.abs(_polyval_monic(coef[:, bad], b[bad]))
-                    floor = 1e-12 * scale[bad] ** rows
-                    assert np.all(res_a <= 16 * res_b + floor), \
-                        f"{what}: root {k} at {bad[:5]} is a worse root than the reference's: {res_a[:5]} vs {res_b[:5]}"
-    assert outliers <= max(1, 1e-4 * n), f"{what}: {outliers} ill-conditioned outliers in {n} cases"
+            err = np.abs(a - b)
+            rel = err / np.maximum(np.maximum(np.abs(a), np.abs(b)), scale)
+            ok = both_nan | same_inf | (rel <= REL_TOL) | (err <= allow) | ~live
+            bad = np.flatnonzero(~ok & ~fragile)
+            assert bad.size == 0, (f"{what}: root {k} differs beyond 1e-9 relative and beyond its conditioning at {bad[:5]}: "
+                                   f"{a[bad[:5]]} vs {b[bad[:5]]}, cond {cond[bad[:5]]}")
+            fr = np.flatnonzero(~ok & fragile)
+            if fr.size and (rows == 4 or k == 0):  # real roots: ours must be as good a root as the reference's
+                res_a = np.abs(_polyval_monic(coef[:, fr], a[fr]))
+                res_b = np.abs(_polyval_monic(coef[:, fr], b[fr]))
+                floor = 1e-12 * scale[fr] ** rows
+                assert np.all(res_a <= 16 * res_b + floor), \
+                    f"{what}: root {k} at {fr[:5]} is a worse root than the reference's: {res_a[:5]} vs {res_b[:5]}"
+    return {"problems": int(n), "branch_fragile": int(fragile.sum()), "count_differs": int((cnt_a != cnt_b).sum()),
+            "beyond_1e-9": int(sum(((np.abs(roots_a[k] - roots_b[k]) / np.maximum(np.maximum(np.abs(roots_a[k]), np.abs(roots_b[k])), scale)
+                                     > REL_TOL) & keep & ((cnt_a > k) if rows == 4 else True)).sum() for k in range(rows)))}
 
 
 def degenerate_case():
