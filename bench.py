@@ -488,6 +488,124 @@ def c5_block(rig: Rig, steps: int) -> dict:
     return out
 
 
+def f_rows_block(rig: Rig, steps: int) -> dict:
+    """SURVEY section 8(f) rows beside the headline, on c3's candidates (2^20, resident in HBM) and obstacle table:
+    feas   rqcd_check_input_feasibility = RapidTrajectoryGenerator::CheckInputFeasibility(5, 30, 20, 0.002) per candidate
+    planes rqcd_generate_check_planes   = CollisionChecker::CollisionCheck(Boundary) against the six faces of a box
+    plan   rqcd_plan_best               = cost prune -> input feasibility -> planes -> obstacles -> cheapest survivor
+    Each: device-timed throughput, the CPU checker on a sample beside it, parity of the sample, algorithmic flops."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import binding as B
+    from rapidquadcoptercollisiondetection_b200 import abi, workloads as W
+    torch = rig.torch
+    res = Resident(rig, "c3")
+    n, lib, h = res.n, rig.ctx.lib, rig.ctx.h
+    inp = abi.BcSoa(res.d_bc.data_ptr(), n, abi.GOAL_ALL, 0, 0, 0)
+    grav = (C.c_double * 3)(0.0, 0.0, -9.81)
+    d_feas = torch.empty(n, dtype=torch.uint8, device=rig.dev)
+    d_hit = torch.empty(n, dtype=torch.uint8, device=rig.dev)
+    d_stage = torch.empty(n, dtype=torch.uint8, device=rig.dev)
+    box = np.array([[5, 0, 0, -1, 0, 0], [-5, 0, 0, 1, 0, 0], [0, 5, 0, 0, -1, 0], [0, -5, 0, 0, 1, 0],
+                    [0, 0, 5, 0, 0, -1], [0, 0, -5, 0, 0, 1]], dtype=np.float64)  # inside = the normal's side
+    prm = abi.PlanParams()
+    prm.max_cost, prm.check_input = 200.0, 1
+    prm.gravity[:] = [0.0, 0.0, -9.81]
+    prm.fmin, prm.fmax, prm.wmax, prm.min_time_section = 5.0, 30.0, 20.0, MIN_T
+    prm.planes, prm.n_planes = box.ctypes.data, 6
+    summ = abi.Summary()
+
+    def feas():
+        assert lib.rqcd_check_input_feasibility(h, C.byref(inp), n, grav, 5.0, 30.0, 20.0, MIN_T, None, abi.F_DEVICE_PTRS,
+                                                C.c_void_p(d_feas.data_ptr())) == abi.OK
+
+    def planes():
+        assert lib.rqcd_generate_check_planes(h, C.byref(inp), n, C.c_void_p(box.ctypes.data), 6, abi.F_DEVICE_PTRS,
+                                              C.c_void_p(d_hit.data_ptr()), None) == abi.OK
+
+    def plan():
+        assert lib.rqcd_plan_best(h, C.byref(inp), n, C.byref(prm), abi.F_DEVICE_PTRS, 0, C.c_void_p(d_stage.data_ptr()),
+                                  C.byref(summ)) == abi.OK
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        rig.barrier()
+        l0 = rig.ctx.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(rig.stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(rig.stream)
+        rig.barrier()
+        return ev0.elapsed_time(ev1) / steps, (rig.ctx.launch_count() - l0) // steps
+
+    orc = B.Oracle()
+    impl, kind = cpu_checker()
+    threads = os.cpu_count() or 1
+    ns = 1 << 16
+    bc_s = W.synth_bc(WORKLOADS["c3"]["seed"], res.lo, ns)
+    peaks = rig.ctx.measure_fp64_peak(100)
+    peak_tf = peaks["dmul_dadd_flops"] / 1e12
+    out = {"candidates": n, "steps": steps, "peak_tflops_dmul_dadd": peak_tf}
+
+    # ---- feas
+    ms, launches = timed(feas)
+    orc.feas_counters()
+    want = orc.input_feasibility(bc_s)
+    sec, axis_it, full = orc.feas_counters()
+    # algorithmic flops per candidate: 3 x 59 (alpha, beta, gamma: a1) + 3 x 10 (peak times) + per section entered 1 + 4
+    # GetThrust (42 each) + per axis bound 71 (4-6 acceleration values, 2-3 jerk values, squares) + 8 per completed section
+    flops = 207.0 + (sec * 169.0 + axis_it * 71.0 + full * 8.0) / ns
+    nc = 1 << 18
+    bc_c = W.synth_bc(WORKLOADS["c3"]["seed"], res.lo, nc)
+    parts = np.array_split(np.arange(nc), threads * 4)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda ix: impl.input_feasibility(np.ascontiguousarray(bc_c[:, ix[0]:ix[-1] + 1])), parts))
+    dt = time.perf_counter() - t0
+    out["feas"] = {"what": "CheckInputFeasibility(5, 30, 20, 0.002) per candidate (RapidTrajectoryGenerator.cpp:74-160)",
+                   "value": n / (ms * 1e-3), "unit": "candidates/s", "ms_per_step": ms, "gpu_launches_per_step": launches,
+                   "parity_mismatches_vs_oracle_sample": int((d_feas[:ns].cpu().numpy() != want).sum()), "oracle_sample": ns,
+                   "result_counts": np.bincount(d_feas.cpu().numpy(), minlength=5).tolist(),
+                   "sections_per_candidate": sec / ns, "flops_per_candidate": flops,
+                   "roofline": {"bound": "fp64", "achieved": flops * n / (ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                                "frac": flops * n / (ms * 1e-3) / 1e12 / peak_tf},
+                   "cpu_baseline": {"value": nc / dt, "unit": "candidates/s", "cores": threads, "kind": kind,
+                                    "sample": f"first {nc} candidates, {dt:.2f} s wall"}}
+    # ---- planes
+    ms, launches = timed(planes)
+    got = d_hit[:ns].cpu().numpy()
+    gen = orc.generate(bc_s)
+    wv, _ = orc.check_planes(gen["coeffs"], bc_s[18], box)
+    t0 = time.perf_counter()
+    gen_c = orc.generate(bc_c)
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda ix: orc.check_planes(np.ascontiguousarray(gen_c["coeffs"][:, ix[0]:ix[-1] + 1]),
+                                                np.ascontiguousarray(bc_c[18, ix[0]:ix[-1] + 1]), box), parts))
+    dt = time.perf_counter() - t0
+    fl = 34.0 + 70.0 + 3.4 * 68.0 + 210.0 / 6
+    out["planes"] = {"what": "CollisionCheck(Boundary) x 6 box faces per candidate, documented intent (CollisionChecker.cpp:25-68)",
+                     "value": 6 * n / (ms * 1e-3), "unit": "trajectory-plane checks/s", "ms_per_step": ms,
+                     "gpu_launches_per_step": launches, "parity_mismatches_vs_oracle_sample": int((got != wv).sum()),
+                     "oracle_sample": ns, "hit_fraction": float(d_hit.float().mean().item()),
+                     "flops_per_check_estimate": fl,
+                     "roofline": {"bound": "fp64", "achieved": fl * 6 * n / (ms * 1e-3) / 1e12, "peak": peak_tf,
+                                  "unit": "TFLOP/s", "frac": fl * 6 * n / (ms * 1e-3) / 1e12 / peak_tf},
+                     "cpu_baseline": {"value": 6 * nc / dt, "unit": "trajectory-plane checks/s", "cores": threads, "kind": "port",
+                                      "sample": f"first {nc} candidates incl. generation, {dt:.2f} s wall"}}
+    # ---- plan
+    ms, launches = timed(plan)
+    stage = d_stage.cpu().numpy()
+    out["plan"] = {"what": "rqcd_plan_best: cost <= 200 -> input feasible -> inside the box -> 64 obstacles -> cheapest survivor",
+                   "value": n / (ms * 1e-3), "unit": "candidates/s", "ms_per_step": ms, "gpu_launches_per_step": launches,
+                   "stage_counts": np.bincount(stage, minlength=7).tolist(), "best": summ.as_dict()}
+    del res
+    torch.cuda.empty_cache()
+    return out
+
+
 def torch_index(rig: Rig, idx):
     return rig.torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(rig.dev)
 
@@ -594,6 +712,8 @@ def main():
         blk = c5_block(rig, 3)
         if line is not None:
             line["c5"] = blk
+        if world == 1 and line is not None:
+            line["f_rows"] = f_rows_block(rig, 10)
     if line is not None:
         emit(line)
     rig.close()

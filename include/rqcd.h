@@ -159,6 +159,7 @@ typedef struct rqcd_out {
                               the call synchronises the context's stream before returning. */
   uint8_t* fragile;        /* [n], with RQCD_F_FRAGILE (required then): 1 when the trajectory's verdict or first obstacle
                               may depend on the last bits of the cubic solver's acos / cos / pow, see the flag */
+  uint8_t* input_feasibility; /* [n], optional, with rqcd_set_input_filter: each candidate's rqcd_input_feasibility */
   double* params;          /* rqcd_generate only: RQCD_PARAM_ROWS rows alpha x,y,z, beta x,y,z, gamma x,y,z =
                               GetAxisParamAlpha/Beta/Gamma(axis) (RapidTrajectoryGenerator.hpp:219-229); may be NULL */
   int64_t param_stride;
@@ -285,6 +286,20 @@ int rqcd_generate_check_planes(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, 
 int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const double* gravity, double fmin,
                            double fmax, double wmax, double min_time_section, const int64_t* group, uint32_t flags,
                            uint8_t* result);
+
+/* The same test as a FILTER inside the generate + check calls -- what both drivers do between Generate and CollisionCheck
+ * (PerformanceEval.cpp:163-173 keeps only InputFeasible trials; a fresh generator object per candidate). While a filter is
+ * set, rqcd_generate_check and rqcd_generate_check_pairwise first run CheckInputFeasibility(fmin, fmax, wmax,
+ * min_time_section) on every candidate; a candidate that is not InputFeasible is NOT checked and NOT counted in the
+ * summary, its verdict is RQCD_NOT_CHECKED, its first_obstacle -2, its row of the verdict matrix is not written.
+ * rqcd_out::input_feasibility (optional) receives the per-candidate result. limits == NULL switches the filter off. */
+typedef struct rqcd_input_limits {
+  double gravity[3];
+  double fmin, fmax, wmax;   /* CheckInputFeasibility(fminAllowed, fmaxAllowed, wmaxAllowed, .) */
+  double min_time_section;
+} rqcd_input_limits;
+#define RQCD_NOT_CHECKED 255
+int rqcd_set_input_filter(rqcd_ctx* ctx, const rqcd_input_limits* limits);
 
 /* ---- the planner's candidate loop ----------------------------------------------
  * The reference ships the stages but not the loop that chains them (its docs describe one, StoppingTrajFinder::

@@ -184,6 +184,12 @@ class _CpuImpl:
                                      C.c_double(wmax), C.c_double(min_t), _ptr(group), _ptr(res))
         return res
 
+    def feas_counters(self, reset=True):
+        """(sections, axis evaluations, full sections) of input_feasibility calls since the last reset (oracle only)."""
+        out = (C.c_uint64 * 3)()
+        self._f("feas_counters")(out, C.c_int(1 if reset else 0))
+        return [int(x) for x in out]
+
     def rotation_matrix(self, quat):
         q = np.asarray(quat, dtype=np.float64)
         R = np.empty(9)

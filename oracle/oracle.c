@@ -862,14 +862,23 @@ static double thrust(const feas_ctx* f, double t) { /* RapidTrajectoryGenerator.
   return v3_norm(a);
 }
 
+/* work counters of the feasibility recursion (flop model of bench.py's `feas` block; single-threaded use only) */
+static uint64_t g_feas_sections, g_feas_axis_iters, g_feas_full;
+void orc_feas_counters(uint64_t out[3], int reset) {
+  out[0] = g_feas_sections, out[1] = g_feas_axis_iters, out[2] = g_feas_full;
+  if (reset) g_feas_sections = g_feas_axis_iters = g_feas_full = 0;
+}
+
 static int feas_section(feas_ctx* f, double fminA, double fmaxA, double wmaxA, double t1, double t2,
                         double minT) { /* RapidTrajectoryGenerator.cpp:74-147 */
+  g_feas_sections++;
   if (t2 - t1 < minT) return RQCD_INPUT_INDETERMINABLE;
   if (dmax(thrust(f, t1), thrust(f, t2)) > fmaxA) return RQCD_INPUT_INFEASIBLE_THRUST_HIGH;
   if (dmin(thrust(f, t1), thrust(f, t2)) < fminA) return RQCD_INPUT_INFEASIBLE_THRUST_LOW;
   double fminSqr = 0, fmaxSqr = 0, jmaxSqr = 0;
   for (int i = 0; i < 3; i++) {
     double amin, amax;
+    g_feas_axis_iters++;
     minmax_acc(&f->ax[i], f->peak[i], &f->peak_init[i], &amin, &amax, t1, t2);
     double v1 = amin - f->grav[i];
     double v2 = amax - f->grav[i];
@@ -882,6 +891,7 @@ static int feas_section(feas_ctx* f, double fminA, double fmaxA, double wmaxA, d
     fmaxSqr += sq(dmax(fabs(v1), fabs(v2)));
     jmaxSqr += max_jerk_sq(&f->ax[i], t1, t2);
   }
+  g_feas_full++;
   double fmin = sqrt(fminSqr);
   double fmax = sqrt(fmaxSqr);
   double wBound;

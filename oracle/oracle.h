@@ -77,6 +77,8 @@ void orc_input_feasibility(const rqcd_bc_soa* in, int64_t n, const double gravit
                            double wmax, double min_time_section, const int64_t* group, uint8_t* result);
 
 /* splitmix64 counter-based synthetic boundary conditions (same function as rqcd_synth_bc). */
+/* sections entered, per-axis bound evaluations, sections that reached the rate bound -- since the last reset */
+void orc_feas_counters(uint64_t out[3], int reset);
 void orc_synth_bc(uint64_t seed, int64_t index_base, int64_t n, double* bc, int64_t stride);
 
 /* The reference drivers' input streams: mt19937(0) + libstdc++ uniform_real_distribution<double>.

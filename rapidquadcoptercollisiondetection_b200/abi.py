@@ -98,6 +98,14 @@ class PlanParams(C.Structure):
     ]
 
 
+class InputLimits(C.Structure):
+    _fields_ = [("gravity", C.c_double * 3), ("fmin", C.c_double), ("fmax", C.c_double), ("wmax", C.c_double),
+                ("min_time_section", C.c_double)]
+
+
+NOT_CHECKED = 255
+
+
 class Out(C.Structure):
     _fields_ = [
         ("verdict", C.c_void_p),
@@ -108,6 +116,7 @@ class Out(C.Structure):
         ("coeff_stride", C.c_int64),
         ("summary", C.POINTER(Summary)),
         ("fragile", C.c_void_p),
+        ("input_feasibility", C.c_void_p),
         ("params", C.c_void_p),
         ("param_stride", C.c_int64),
     ]
@@ -128,6 +137,7 @@ SYMBOLS = {
     "rqcd_launch_count": (C.c_uint64, [_VP]),
     "rqcd_last_kernel_name": (C.c_char_p, [_VP]),
     "rqcd_fragile_reasons": (C.c_int, [_VP, _VP]),
+    "rqcd_set_input_filter": (C.c_int, [_VP, C.POINTER(InputLimits)]),
     "rqcd_set_obstacles": (C.c_int, [_VP, C.POINTER(Obstacle), C.c_int32]),
     "rqcd_num_obstacles": (C.c_int32, [_VP]),
     "rqcd_generate": (C.c_int, [_VP, C.POINTER(BcSoa), C.c_int64, C.c_uint32, C.POINTER(Out)]),

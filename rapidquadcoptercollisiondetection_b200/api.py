@@ -115,6 +115,19 @@ class Context:
         self._chk(self.lib.rqcd_fragile_reasons(self.h, _ptr(out)))
         return out
 
+    def set_input_filter(self, gravity=(0.0, 0.0, -9.81), fmin=5.0, fmax=30.0, wmax=20.0, min_t=0.002, on=True):
+        """rqcd_set_input_filter: generate_check / generate_check_pairwise then skip (verdict 255) the candidates that are
+        not InputFeasible, like PerformanceEval.cpp:163-173; on=False switches it off."""
+        if not on:
+            self._chk(self.lib.rqcd_set_input_filter(self.h, None))
+            self._filter = False
+            return
+        lim = abi.InputLimits()
+        lim.gravity[:] = [float(x) for x in gravity]
+        lim.fmin, lim.fmax, lim.wmax, lim.min_time_section = float(fmin), float(fmax), float(wmax), float(min_t)
+        self._chk(self.lib.rqcd_set_input_filter(self.h, C.byref(lim)))
+        self._filter = True
+
     def read_summary(self) -> dict:
         s = abi.Summary()
         self._chk(self.lib.rqcd_read_summary(self.h, C.byref(s)), allow=(abi.ERR_DEPTH_CAP,))
@@ -152,6 +165,8 @@ class Context:
 
     def _host_out(self, n, m, matrix, coeffs, first=True, fragile=False):
         res = {"verdict": np.full(n, 255, dtype=np.uint8)}
+        if getattr(self, "_filter", False):
+            res["input_feasibility"] = np.full(n, 255, dtype=np.uint8)
         if fragile:
             res["fragile"] = np.full(n, 255, dtype=np.uint8)
         if first:
@@ -165,7 +180,7 @@ class Context:
         out = abi.Out(verdict=_ptr(res["verdict"]), first_obstacle=_ptr(res.get("first_obstacle")),
                       verdict_matrix=_ptr(res.get("verdict_matrix")), cost=_ptr(res.get("cost")),
                       coeffs=_ptr(res.get("coeffs")), coeff_stride=n, summary=C.pointer(summ),
-                      fragile=_ptr(res.get("fragile")))
+                      fragile=_ptr(res.get("fragile")), input_feasibility=_ptr(res.get("input_feasibility")))
         return res, out, summ
 
     def generate_check(self, bc, min_t, goal_mask=abi.GOAL_ALL, flags=0, index_base=0, matrix=True, n=None, shared_rows=0,

@@ -304,6 +304,34 @@ int validate_out(const rqcd_out* out, uint32_t flags, long long n) {
   return RQCD_OK;
 }
 
+int outputs_d2h(rqcd_ctx* ctx, const rqcd_out* out, long long n, int m, const OutStage& o) {
+  cudaStream_t cs = ctx->stream;
+  if (n > 0) {
+    if (o.verdict && out->verdict) RQCD_CU(cudaMemcpyAsync(out->verdict, o.verdict, (size_t)n, cudaMemcpyDeviceToHost, cs));
+    if (o.first && out->first_obstacle)
+      RQCD_CU(cudaMemcpyAsync(out->first_obstacle, o.first, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
+    if (o.matrix && m > 0)
+      RQCD_CU(cudaMemcpyAsync(out->verdict_matrix, o.matrix, (size_t)n * (size_t)m, cudaMemcpyDeviceToHost, cs));
+    if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost, o.cost, (size_t)n * 8, cudaMemcpyDeviceToHost, cs));
+    if (o.coeffs) RQCD_CU(rows_d2h(out->coeffs, out->coeff_stride, o.coeffs, n, RQCD_COEFF_ROWS, cs));
+  }
+  return RQCD_OK;
+}
+
+// The input filter of the generate + check calls (rqcd_set_input_filter): CheckInputFeasibility for every candidate, the
+// step both drivers take between Generate and CollisionCheck (PerformanceEval.cpp:163-173). The result doubles as the
+// check kernels' skip mask: a candidate that is not InputFeasible is neither checked nor counted.
+int run_input_filter(rqcd_ctx* ctx, CheckCall& cc, const OutStage& o, long long n, uint8_t* d_feas) {
+  const rqcd_input_limits& L = ctx->filter;
+  CheckParams q = cc.p;
+  q.progress = nullptr;
+  RQCD_CU(launch_feasibility(q, L.gravity, L.fmin, L.fmax, L.wmax, L.min_time_section, nullptr, nullptr, d_feas, o.verdict,
+                             cc.pairwise ? nullptr : o.first, ctx->stream));
+  ctx->launches++;
+  cc.p.skip = d_feas;
+  return RQCD_OK;
+}
+
 // Host-pointer call: ONE persistent launch over the whole range that starts as soon as the first chunk of
 // boundary conditions has crossed PCIe. The remaining chunks follow on the copy stream while the kernel runs; after
 // each chunk the copy engine advances a progress word in device memory (an 8-byte copy from pinned memory -- no SM
@@ -362,14 +390,8 @@ int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long lo
   cc.p.progress = nullptr;
   cc.p.stream_error = nullptr;
   if (st != RQCD_OK) return st;
-  if (n > 0) {
-    if (o.verdict) RQCD_CU(cudaMemcpyAsync(out->verdict, o.verdict, (size_t)n, cudaMemcpyDeviceToHost, cs));
-    if (o.first) RQCD_CU(cudaMemcpyAsync(out->first_obstacle, o.first, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
-    if (o.matrix && m > 0)
-      RQCD_CU(cudaMemcpyAsync(out->verdict_matrix, o.matrix, (size_t)n * (size_t)m, cudaMemcpyDeviceToHost, cs));
-    if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost, o.cost, (size_t)n * 8, cudaMemcpyDeviceToHost, cs));
-    if (o.coeffs) RQCD_CU(rows_d2h(out->coeffs, out->coeff_stride, o.coeffs, n, RQCD_COEFF_ROWS, cs));
-  }
+  st = outputs_d2h(ctx, out, n, m, o);
+  if (st != RQCD_OK) return st;
   RQCD_CU(cudaMemcpyAsync(ctx->h_stream + kMaxChunks, ctx->d_stream + 1, sizeof(unsigned long long),
                           cudaMemcpyDeviceToHost, cs));
   RQCD_CU(cudaStreamSynchronize(cs));
@@ -438,7 +460,26 @@ int finish_check(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, uint32_t fla
   }
   fill_params_out(cc.p, o);
   cc.p.early_exit = (flags & RQCD_F_EARLY_EXIT) ? 1 : 0;
-  int st = dev ? run_check(ctx, cc) : run_host_pipeline(ctx, cc, out, n, m, o);
+  int st;
+  const bool filter = ctx->filter_on && cc.mode == MODE_BC && n > 0;
+  if (filter) {
+    uint8_t* d_feas = dev ? out->input_feasibility : nullptr;
+    if (!d_feas) {
+      RQCD_CU(ensure(ctx->s_feas, (size_t)n));
+      d_feas = (uint8_t*)ctx->s_feas.p;
+    }
+    // the filter reads every candidate before the check starts: the input goes over in full first (no streaming)
+    if (!dev) RQCD_CU(copy_blocks(cc, n, ctx->stream));
+    st = run_input_filter(ctx, cc, o, n, d_feas);
+    if (st == RQCD_OK) st = run_check(ctx, cc);
+    if (st == RQCD_OK && !dev) {
+      st = outputs_d2h(ctx, out, n, m, o);
+      if (st == RQCD_OK && out->input_feasibility)
+        RQCD_CU(cudaMemcpyAsync(out->input_feasibility, d_feas, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  } else {
+    st = dev ? run_check(ctx, cc) : run_host_pipeline(ctx, cc, out, n, m, o);
+  }
   if (st != RQCD_OK) return st;
   int sum_st = RQCD_OK;
   if (out->summary) {
@@ -454,6 +495,7 @@ int finish_check(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, uint32_t fla
         RQCD_CU(cudaMemcpyAsync(out->verdict_matrix, o.matrix, (size_t)n * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
     }
   }
+  cc.p.skip = nullptr;
   if (!dev) RQCD_CU(cudaStreamSynchronize(ctx->stream));
   return sum_st;
 }
@@ -542,7 +584,7 @@ void rqcd_destroy(rqcd_ctx* ctx) {
   release(ctx->obs_blob);
   DevBuf* bufs[] = {&ctx->s_in,     &ctx->s_aux,   &ctx->s_verdict, &ctx->s_first,  &ctx->s_matrix, &ctx->s_cost,
                     &ctx->s_coeffs, &ctx->s_roots, &ctx->s_count,   &ctx->s_planes, &ctx->s_peaks,  &ctx->s_group,
-                    &ctx->s_fragile};
+                    &ctx->s_fragile, &ctx->s_feas};
   for (DevBuf* b : bufs) release(*b);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->d_why) cudaFree(ctx->d_why);
@@ -607,6 +649,18 @@ int rqcd_read_summary(rqcd_ctx* ctx, rqcd_summary* out) {
 }
 
 uint64_t rqcd_launch_count(const rqcd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rqcd_set_input_filter(rqcd_ctx* ctx, const rqcd_input_limits* limits) {
+  if (!ctx) return RQCD_ERR_INVALID_ARG;
+  if (!limits) {
+    ctx->filter_on = false;
+    return RQCD_OK;
+  }
+  if (bad_min_t(limits->min_time_section)) return RQCD_ERR_INVALID_ARG;
+  ctx->filter = *limits;
+  ctx->filter_on = true;
+  return RQCD_OK;
+}
 
 const char* rqcd_last_kernel_name(const rqcd_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
 
@@ -935,7 +989,7 @@ int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n
   }
   if (group) RQCD_CU(ensure(ctx->s_peaks, (size_t)n * 8 * 6));
   RQCD_CU(launch_feasibility(p, gravity, fmin, fmax, wmax, min_time_section, dgroup, (double*)ctx->s_peaks.p, dres,
-                             ctx->stream));
+                             nullptr, nullptr, ctx->stream));
   ctx->launches += group ? 2 : 1;
   if (!dev) {
     RQCD_CU(cudaMemcpyAsync(result, dres, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -979,7 +1033,7 @@ int rqcd_plan_best(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const rqcd_p
   // stage 1: CheckInputFeasibility
   if (prm->check_input && n > 0) {
     RQCD_CU(launch_feasibility(p, prm->gravity, prm->fmin, prm->fmax, prm->wmax, prm->min_time_section, nullptr, nullptr,
-                               d_feas, s));
+                               d_feas, nullptr, nullptr, s));
     ctx->launches++;
   }
   // stage 2: plane boundaries

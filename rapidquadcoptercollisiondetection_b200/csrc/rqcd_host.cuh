@@ -49,7 +49,9 @@ struct rqcd_ctx {
   rqcd::DevSummary* d_merged = nullptr;  // merge of the table (rqcd_exchange_summaries)
   bool merged_valid = false;
   // staging for host-pointer calls
-  rqcd::DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group, s_fragile;
+  rqcd::DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group, s_fragile, s_feas;
+  bool filter_on = false;  // rqcd_set_input_filter
+  rqcd_input_limits filter = {};
   int refill_min = 0;  // RQCD_REFILL_MIN override; 0 = chosen from the obstacle count
   int lockstep = -1;   // RQCD_LOCKSTEP override (0/1); -1 = chosen from the obstacle count
   int pool = 1;        // RQCD_POOL (0/1): k_pool (staged sections, certified solver skip) for obstacle tables

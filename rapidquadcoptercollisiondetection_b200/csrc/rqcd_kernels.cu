@@ -931,7 +931,9 @@ __global__ void __launch_bounds__(128) k_feas_group_peaks(const CheckParams p, c
   }
 }
 
-__global__ void __launch_bounds__(128) k_feas(const CheckParams p, const FeasArgs fa, const double* peaks, uint8_t* result) {
+// verdict / first (may be null): outputs of the check that follows, pre-filled for the candidates the filter rejects
+__global__ void __launch_bounds__(128) k_feas(const CheckParams p, const FeasArgs fa, const double* peaks, uint8_t* result,
+                                              uint8_t* verdict, int* first) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     AxisState ax[3];
     double Tf;
@@ -967,6 +969,10 @@ __global__ void __launch_bounds__(128) k_feas(const CheckParams p, const FeasArg
       }
     }
     result[i] = (uint8_t)res;
+    if (res != RQCD_INPUT_FEASIBLE_) {
+      if (verdict) verdict[i] = (uint8_t)255;  // RQCD_NOT_CHECKED
+      if (first) first[i] = -2;
+    }
   }
 }
 
@@ -1208,7 +1214,8 @@ cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, 
 }
 
 cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], double fmin, double fmax, double wmax,
-                               double min_t, const long long* group, double* peaks, uint8_t* result, cudaStream_t s) {
+                               double min_t, const long long* group, double* peaks, uint8_t* result, uint8_t* verdict, int* first,
+                               cudaStream_t s) {
   if (p.n <= 0) return cudaSuccess;
   FeasArgs fa;
   for (int k = 0; k < 3; k++) fa.grav[k] = grav[k];
@@ -1219,7 +1226,7 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  k_feas<<<grid, 128, 0, s>>>(p, fa, group ? peaks : nullptr, result);
+  k_feas<<<grid, 128, 0, s>>>(p, fa, group ? peaks : nullptr, result, verdict, first);
   return cudaGetLastError();
 }
 

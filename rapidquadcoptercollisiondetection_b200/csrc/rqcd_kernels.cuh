@@ -114,7 +114,8 @@ cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, 
                           cudaStream_t s);
 // group may be null; peaks: scratch of 6*n doubles, needed when group is given
 cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], double fmin, double fmax, double wmax,
-                               double min_t, const long long* group, double* peaks, uint8_t* result, cudaStream_t s);
+                               double min_t, const long long* group, double* peaks, uint8_t* result, uint8_t* verdict,
+                               int* first, cudaStream_t s);
 // planner glue (rqcd_plan_best): stage codes, see rqcd_plan_stage in rqcd.h
 cudaError_t launch_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas, const uint8_t* plane_hit,
                              uint8_t* stage, cudaStream_t s);

@@ -133,6 +133,62 @@ def arrays_to_specs(a, prefix: str = "") -> list:
     return specs
 
 
+# ---- the reference drivers' own input streams: std::mt19937(0) + libstdc++ uniform_real_distribution<double> --------
+def mt19937_canonical(n: int, seed: int = 0) -> np.ndarray:
+    """n draws of std::generate_canonical<double, 53>(std::mt19937(seed)) as libstdc++ computes it: two 32-bit outputs per
+    value, low word first, (g1 + g2 * 2^32) / 2^64 in double arithmetic (a result that rounds to 1 becomes
+    nextafter(1, 0)). numpy's MT19937 with the legacy seeding is init_genrand(seed), the engine's own seeding."""
+    bg = np.random.MT19937()
+    bg._legacy_seeding(seed)
+    raw = bg.random_raw(2 * n).astype(np.float64)
+    ret = (raw[0::2] + raw[1::2] * 4294967296.0) / 18446744073709551616.0
+    ret[ret >= 1.0] = np.nextafter(1.0, 0.0)
+    return ret
+
+
+def c1_trials(n_trials: int):
+    """The first n_trials trials of test/PerformanceEval.cpp:117-148, accepted or not: 20 draws each in the order
+    vel0, acc0, posf, velf, accf (3 each, U(-4, 4); g++ evaluates the three constructor arguments right to left, so
+    the first draw of a vector is its z), Tf U(0.2, 4), obstacle position (3), radius U(0.1, 1.5); pos0 = 0.
+    Returns (bc 19 x n, spheres 4 x n). The driver keeps the trials that pass CheckInputFeasibility(5, 30, 20, 0.002)
+    until it has 10^7 of them: that takes 15 571 728 trials (tests/golden/golden_counts.json: c1_trials)."""
+    u = mt19937_canonical(20 * n_trials).reshape(n_trials, 20)
+    bc = np.zeros((abi.BC_ROWS, n_trials))
+    sph = np.empty((4, n_trials))
+    sym = lambda x: x * 8.0 + -4.0  # noqa: E731  uniform_real_distribution: canonical * (b - a) + a
+    for v, row in enumerate((abi.BC_V0, abi.BC_A0, abi.BC_PF, abi.BC_VF, abi.BC_AF)):
+        for k in range(3):
+            bc[row + 2 - k] = sym(u[:, 3 * v + k])
+    bc[abi.BC_TF] = u[:, 15] * (4.0 - 0.2) + 0.2
+    for k in range(3):
+        sph[2 - k] = sym(u[:, 16 + k])
+    sph[3] = u[:, 19] * (1.5 - 0.1) + 0.1
+    return bc, sph
+
+
+def c2_candidates(n_batches: int, per_batch: int = 100) -> np.ndarray:
+    """test/ForestPerformanceEval.cpp:167-193: per batch vel0 = (U[2,8], U+-2, U+-2), acc0 = (U[4,10], U+-2, U+-2) (z drawn
+    first), pos0 = (-2.5, 0, 0); per candidate posf U(+-2.5)^3 (z first) and Tf U[0.5, 2]; goal velocity = acceleration = 0.
+    Returns bc 19 x (n_batches * per_batch), candidates of a batch contiguous."""
+    per = 6 + 4 * per_batch
+    u = mt19937_canonical(per * n_batches).reshape(n_batches, per)
+    n = n_batches * per_batch
+    bc = np.zeros((abi.BC_ROWS, n))
+    bc[abi.BC_P0] = -2.5
+    rep = lambda x: np.repeat(x, per_batch)  # noqa: E731
+    bc[abi.BC_V0 + 2] = rep(u[:, 0] * 4.0 + -2.0)
+    bc[abi.BC_V0 + 1] = rep(u[:, 1] * 4.0 + -2.0)
+    bc[abi.BC_V0 + 0] = rep(u[:, 2] * 6.0 + 2.0)
+    bc[abi.BC_A0 + 2] = rep(u[:, 3] * 4.0 + -2.0)
+    bc[abi.BC_A0 + 1] = rep(u[:, 4] * 4.0 + -2.0)
+    bc[abi.BC_A0 + 0] = rep(u[:, 5] * 6.0 + 4.0)
+    c = u[:, 6:].reshape(n_batches, per_batch, 4)
+    for k in range(3):
+        bc[abi.BC_PF + 2 - k] = (c[:, :, k] * 5.0 + -2.5).reshape(n)
+    bc[abi.BC_TF] = (c[:, :, 3] * 1.5 + 0.5).reshape(n)
+    return bc
+
+
 def forest_obstacles() -> list:
     """The five trees of test/ForestPerformanceEval.cpp:130-136 (two tilted +-45 deg about x)."""
     pos = [(-1.75, 1.5, 0), (0.5, -1.5, 0), (1.5, 0.5, 0), (-1.0, -1.0, 0), (0.0, 0.8, -0.3)]

@@ -31,7 +31,7 @@ def test_struct_mirrors_match_header_sizes():
     # rqcd_obstacle: 2 x int32 + (3+1+3+4+18+2) doubles; rqcd_summary: 9 x 8 bytes + double + int64
     assert C.sizeof(abi.Obstacle) == 8 + 31 * 8
     assert C.sizeof(abi.Summary) == 11 * 8
-    assert C.sizeof(abi.BcSoa) == 40 and C.sizeof(abi.CoeffSoa) == 32 and C.sizeof(abi.Out) == 80
+    assert C.sizeof(abi.BcSoa) == 40 and C.sizeof(abi.CoeffSoa) == 32 and C.sizeof(abi.Out) == 88
 
 
 def test_no_device_means_no_service():

@@ -530,3 +530,46 @@ def test_obstacle_table_limits(ctx, oracle):
         ctx.set_obstacles(abi.make_obstacles(big), 3000)
     assert e.value.status == abi.ERR_UNSUPPORTED
     assert ctx.num_obstacles() == 700  # the previous set stays in place
+
+
+def test_input_filter_reproduces_performance_eval(ctx, oracle):
+    """rqcd_set_input_filter + rqcd_generate_check_pairwise on the driver's own trial stream (accepted or not) = the whole
+    trial loop of test/PerformanceEval.cpp:117-182 on the device: CheckInputFeasibility keeps 64 % of the trials, only those
+    are checked and counted. Against the oracle's filtered stream (pinned to data/PerformanceEval.txt by
+    tests/test_oracle_golden.py): same accepted set, same verdicts."""
+    n_acc = 200_000
+    bc_a, sph_a, trials = oracle.c1_inputs(n_acc, filter=True)   # the accepted trials, in order
+    bc, sph = W.c1_trials(trials)                                # every trial the driver drew to get them
+    ctx.set_input_filter()
+    try:
+        r = ctx.generate_check_pairwise(bc, sph, MIN_T)
+    finally:
+        ctx.set_input_filter(on=False)
+    feas = oracle.input_feasibility(bc)
+    np.testing.assert_array_equal(r["input_feasibility"], feas)
+    keep = feas == 0
+    assert int(keep.sum()) == n_acc and keep[-1]
+    np.testing.assert_array_equal(bc[:, keep], bc_a)
+    o = oracle.generate_check_pairwise(bc_a, sph_a, MIN_T, nthreads=8)
+    np.testing.assert_array_equal(r["verdict"][keep], o["verdict"])
+    assert (r["verdict"][~keep] == abi.NOT_CHECKED).all()
+    assert r["summary"]["traj_counts"] == o["summary"]["traj_counts"]
+    assert r["summary"]["pairs_checked"] == n_acc
+    # the table shape with the filter, early exit (Forest loop with the driver's inputFeas test in front of the check)
+    specs = W.forest_obstacles()
+    obs = abi.make_obstacles(specs)
+    ctx.set_obstacles(obs, len(specs))
+    c2 = W.c2_candidates(50)
+    ctx.set_input_filter()
+    try:
+        f = ctx.generate_check(c2, MIN_T, flags=abi.F_EARLY_EXIT)
+    finally:
+        ctx.set_input_filter(on=False)
+    fe = oracle.input_feasibility(c2)   # a fresh object per candidate (the filter's semantics)
+    np.testing.assert_array_equal(f["input_feasibility"], fe)
+    k2 = fe == 0
+    o2 = oracle.generate_check(np.ascontiguousarray(c2[:, k2]), obs, len(specs), MIN_T, flags=abi.F_EARLY_EXIT, matrix=False, nthreads=4)
+    np.testing.assert_array_equal(f["verdict"][k2], o2["verdict"])
+    np.testing.assert_array_equal(f["first_obstacle"][k2], o2["first_obstacle"])
+    assert (f["verdict"][~k2] == abi.NOT_CHECKED).all() and (f["first_obstacle"][~k2] == -2).all()
+    assert f["summary"]["traj_counts"] == o2["summary"]["traj_counts"]
