@@ -325,6 +325,7 @@ int run_input_filter(rqcd_ctx* ctx, CheckCall& cc, const OutStage& o, long long 
   const rqcd_input_limits& L = ctx->filter;
   CheckParams q = cc.p;
   q.progress = nullptr;
+  q.work_counter = ctx->d_counter;
   RQCD_CU(launch_feasibility(q, L.gravity, L.fmin, L.fmax, L.wmax, L.min_time_section, nullptr, nullptr, d_feas, o.verdict,
                              cc.pairwise ? nullptr : o.first, ctx->stream));
   ctx->launches++;
@@ -988,6 +989,7 @@ int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n
     dres = (uint8_t*)ctx->s_verdict.p;
   }
   if (group) RQCD_CU(ensure(ctx->s_peaks, (size_t)n * 8 * 6));
+  p.work_counter = ctx->d_counter;
   RQCD_CU(launch_feasibility(p, gravity, fmin, fmax, wmax, min_time_section, dgroup, (double*)ctx->s_peaks.p, dres,
                              nullptr, nullptr, ctx->stream));
   ctx->launches += group ? 2 : 1;
@@ -1031,6 +1033,7 @@ int rqcd_plan_best(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const rqcd_p
   RQCD_CU(launch_generate(p, d_cost, nullptr, 0, nullptr, 0, s));
   ctx->launches += n > 0;
   // stage 1: CheckInputFeasibility
+  p.work_counter = ctx->d_counter;
   if (prm->check_input && n > 0) {
     RQCD_CU(launch_feasibility(p, prm->gravity, prm->fmin, prm->fmax, prm->wmax, prm->min_time_section, nullptr, nullptr,
                                d_feas, nullptr, nullptr, s));

@@ -931,47 +931,121 @@ __global__ void __launch_bounds__(128) k_feas_group_peaks(const CheckParams p, c
   }
 }
 
-// verdict / first (may be null): outputs of the check that follows, pre-filled for the candidates the filter rejects
-__global__ void __launch_bounds__(128) k_feas(const CheckParams p, const FeasArgs fa, const double* peaks, uint8_t* result,
-                                              uint8_t* verdict, int* first) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
-    AxisState ax[3];
-    double Tf;
-    feas_axes(p, i, ax, Tf);
-    if (peaks) {
+// k_feas: CheckInputFeasibility for every candidate. Persistent warps, lane owns candidate: every trip of the warp loop
+// runs ONE CheckInputFeasibilitySection per lane as one instruction stream (feas_frame_sel); a section that has to be
+// split continues with its first half and parks the second on the lane's stack (the reference's recursion order: the
+// second half is only looked at when the first is feasible, RapidTrajectoryGenerator.cpp:149-158). Candidates take 1 to
+// some hundred sections (4.2 on average), so a lane whose candidate is decided takes the next one at once instead of
+// waiting for the slowest of 32 -- from a per-warp QUEUE of ready-made candidates in shared memory: when the queue runs
+// dry the whole warp builds 32 new ones, one per lane and converged (boundary conditions -> alpha, beta, gamma, peak
+// times, and the values every section of the candidate would evaluate again: AxisHoist). Generation thus always runs
+// with 32 busy lanes and the section trips with ~30.
+// verdict / first (may be null): outputs of the check that follows, pre-filled for the candidates the filter rejects.
+constexpr int kFeasRows = 32;  // per queued candidate: 3 x (a0, alpha, beta, gamma) + 3 x (pk0, pk1, AxisHoist) + Tf + index
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const FeasArgs fa, const double* peaks, uint8_t* result,
+                                                    uint8_t* verdict, int* first, int refill) {
+  extern __shared__ __align__(16) double feas_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  double* hoist = feas_smem + threadIdx.x;                                  // [18][128]: this thread's candidate
+  double* queue = feas_smem + 18 * 128 + warp * (kFeasRows * 32);          // [kFeasRows][32]: the warp's queue, slot-major rows
+  AxisState ax[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        ax[k].pk0 = peaks[(2 * k) * p.n + i];
-        ax[k].pk1 = peaks[(2 * k + 1) * p.n + i];
+  for (int k = 0; k < 3; k++) ax[k].a0 = ax[k].a = ax[k].b = ax[k].g = ax[k].pk0 = ax[k].pk1 = 0.0;
+#pragma unroll
+  for (int j = 0; j < 18; j++) hoist[j * 128] = 0.0;
+  double2 stack[kMaxDepth];
+  int sp = 0, q_n = 0;
+  double t1 = 0.0, t2 = 0.0;
+  long long idx = -1;
+  bool have = false, exhausted = false;
+  for (;;) {
+    unsigned idle = __ballot_sync(kFull, !have);
+    if (__popc(idle) >= refill || idle == kFull) {
+      for (int round = 0; round < 2; round++) {
+        // ---- idle lanes pop from the top of the queue
+        const int take_n = min(__popc(idle), q_n);
+        const int rank = __popc(idle & lt_mask);
+        if (!have && rank < take_n) {
+          const double* e = queue + (q_n - 1 - rank);
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            ax[k].a0 = e[(4 * k + 0) * 32], ax[k].a = e[(4 * k + 1) * 32], ax[k].b = e[(4 * k + 2) * 32], ax[k].g = e[(4 * k + 3) * 32];
+          }
+#pragma unroll
+          for (int j = 0; j < 18; j++) hoist[j * 128] = e[(12 + j) * 32];
+          t1 = 0.0, t2 = e[30 * 32], idx = __double_as_longlong(e[31 * 32]), sp = 0, have = true;
+        }
+        q_n -= take_n;
+        __syncwarp();
+        idle = __ballot_sync(kFull, !have);
+        if (idle == 0 || exhausted || round == 1) break;
+        // ---- the queue is empty and lanes are still idle: the whole warp builds the next 32 candidates
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(p.work_counter, 32ull);
+        b = __shfl_sync(kFull, b, 0);
+        if (b + 32ull >= (unsigned long long)p.n) exhausted = true;
+        const long long my = (long long)b + lane;
+        const int made = (b >= (unsigned long long)p.n) ? 0 : (int)min(32ll, p.n - (long long)b);
+        {
+          AxisState nx[3];
+          double Tf = 0.0;
+          feas_axes(p, my < p.n ? my : p.n - 1, nx, Tf);
+          if (peaks && my < p.n) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) nx[k].pk0 = peaks[(2 * k) * p.n + my], nx[k].pk1 = peaks[(2 * k + 1) * p.n + my];
+          }
+          double* e = queue + lane;  // slot = lane; slots [0, made) are valid
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const AxisHoist hk = axis_hoist(nx[k]);
+            e[(4 * k + 0) * 32] = nx[k].a0, e[(4 * k + 1) * 32] = nx[k].a, e[(4 * k + 2) * 32] = nx[k].b, e[(4 * k + 3) * 32] = nx[k].g;
+            e[(12 + 6 * k + 0) * 32] = nx[k].pk0, e[(12 + 6 * k + 1) * 32] = nx[k].pk1;
+            e[(12 + 6 * k + 2) * 32] = hk.ap0, e[(12 + 6 * k + 3) * 32] = hk.ap1;
+            e[(12 + 6 * k + 4) * 32] = hk.tmax, e[(12 + 6 * k + 5) * 32] = hk.jm;
+          }
+          e[30 * 32] = Tf;
+          e[31 * 32] = __longlong_as_double(my);
+        }
+        q_n = made;
+        __syncwarp();
       }
     }
-    // the recursion "first half, then (if feasible) second half" as a stack of pending second halves
-    double2 stack[kMaxDepth];
-    int sp = 0, res;
-    double t1 = 0.0, t2 = Tf;
-    for (;;) {
-      bool reached[3];
-      res = feas_frame(ax, fa.grav, fa.fmin, fa.fmax, fa.wmax, t1, t2, fa.min_t, reached);
+    if (__ballot_sync(kFull, have) == 0) {
+      if (exhausted && q_n == 0) break;
+      continue;
+    }
+    AxisHoist hz[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      ax[k].pk0 = hoist[(6 * k + 0) * 128], ax[k].pk1 = hoist[(6 * k + 1) * 128];
+      hz[k].ap0 = hoist[(6 * k + 2) * 128], hz[k].ap1 = hoist[(6 * k + 3) * 128];
+      hz[k].tmax = hoist[(6 * k + 4) * 128], hz[k].jm = hoist[(6 * k + 5) * 128];
+    }
+    int res = feas_frame_sel(ax, hz, fa.grav, fa.fmin, fa.fmax, fa.wmax, t1, t2, fa.min_t);
+    if (have) {
       if (res == FEAS_SPLIT) {
-        const double th = (t1 + t2) / 2;
         if (sp >= kMaxDepth) {
           res = RQCD_INPUT_INDETERMINABLE_;
-          break;
+        } else {
+          const double th = (t1 + t2) / 2;
+          stack[sp++] = make_double2(th, t2);
+          t2 = th;
         }
-        stack[sp++] = make_double2(th, t2);
-        t2 = th;
       } else if (res == RQCD_INPUT_FEASIBLE_ && sp > 0) {
         const double2 e = stack[--sp];
-        t1 = e.x;
-        t2 = e.y;
-      } else {
-        break;
+        t1 = e.x, t2 = e.y;
+        res = FEAS_SPLIT;  // not done yet
       }
-    }
-    result[i] = (uint8_t)res;
-    if (res != RQCD_INPUT_FEASIBLE_) {
-      if (verdict) verdict[i] = (uint8_t)255;  // RQCD_NOT_CHECKED
-      if (first) first[i] = -2;
+      if (res != FEAS_SPLIT) {
+        result[idx] = (uint8_t)res;
+        if (res != RQCD_INPUT_FEASIBLE_) {
+          if (verdict) verdict[idx] = (uint8_t)255;  // RQCD_NOT_CHECKED
+          if (first) first[idx] = -2;
+        }
+        have = false;
+      }
     }
   }
 }
@@ -1226,8 +1300,29 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  k_feas<<<grid, 128, 0, s>>>(p, fa, group ? peaks : nullptr, result, verdict, first);
-  return cudaGetLastError();
+  cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  static int refill = [] {
+    const char* v = getenv("RQCD_FEAS_REFILL");
+    return (v && atoi(v) >= 1 && atoi(v) <= 32) ? atoi(v) : 2;
+  }();
+  static int blocks_per_sm = [] {
+    const char* v = getenv("RQCD_FEAS_BLOCKS");
+    return (v && atoi(v) >= 1 && atoi(v) <= 16) ? atoi(v) : 8;
+  }();
+  const long long want = (p.n + 127) / 128;
+  const int pgrid = (int)(want < (long long)sm_count() * blocks_per_sm ? want : (long long)sm_count() * blocks_per_sm);
+  static int occ = [] {
+    const char* v = getenv("RQCD_FEAS_OCC");
+    return (v && atoi(v) >= 4 && atoi(v) <= 6) ? atoi(v) : 4;
+  }();
+  const size_t smem = (size_t)(18 * 128 + 4 * kFeasRows * 32) * sizeof(double);
+  const void* fn = occ == 6 ? (const void*)&k_feas<6> : (occ == 5 ? (const void*)&k_feas<5> : (const void*)&k_feas<4>);
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const double* pk = group ? peaks : nullptr;
+  void* args[] = {(void*)&p, (void*)&fa, (void*)&pk, (void*)&result, (void*)&verdict, (void*)&first, (void*)&refill};
+  return cudaLaunchKernel(fn, dim3(pgrid), dim3(128), args, smem, s);
 }
 
 cudaError_t launch_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas, const uint8_t* plane_hit,
