@@ -8,8 +8,10 @@ synthetic candidates. Workloads are the configurations of BASELINE.json / SURVEY
   c3 (default) 2^20 primitives x 64 static obstacles (32 spheres + 32 prisms), all pairs
   c4           2^18 primitives x 32 moving obstacles
   c5           2^26 primitives x 256 static obstacles, sharded by candidate index over the ranks (strong scaling)
-  c1           PerformanceEval shape: trajectory i vs its own sphere i (pairwise), 2^22 unfiltered trials
-  c2           ForestPerformanceEval: 10^4 x 100 candidates x 5 prisms, early exit
+  c1           PerformanceEval with the repo's defaults: the driver's own mt19937(0) trial stream, the input-feasibility filter
+               on the device, trajectory i vs its own sphere i; counts must equal data/PerformanceEval.txt
+  c2           ForestPerformanceEval with the repo's defaults: 10^4 x 100 candidates x 5 prisms, input feasibility with the
+               per-batch generator object, early-exit check; counts must equal data/ForestPerfEval.txt
 With N > 1 (torchrun, one rank per GPU) every rank holds the whole obstacle set and its own candidate shard;
 c3/c4/c1/c2 keep the per-rank batch fixed (weak scaling), c5 splits 2^26 (strong). The only exchange is the
 all-gather of the 88-byte per-shard summaries (verdict counts + best candidate), merged by
@@ -55,8 +57,10 @@ WORKLOADS = {
     "c3": dict(n=1 << 20, m=64, seed=1, obs_seed=2, desc="2^20 primitives x 64 static obstacles (32 spheres + 32 prisms), all pairs", scaling="weak"),
     "c4": dict(n=1 << 18, m=32, seed=3, obs_seed=4, desc="2^18 primitives x 32 moving non-rotating obstacles, all pairs", scaling="weak"),
     "c5": dict(n=1 << 26, m=256, seed=5, obs_seed=6, desc="2^26 primitives x 256 static obstacles (128 spheres + 128 prisms) sharded by candidate index", scaling="strong"),
-    "c1": dict(n=1 << 22, m=1, seed=7, obs_seed=8, desc="PerformanceEval shape: 2^22 unfiltered trials, trajectory i vs its own sphere i", scaling="weak"),
-    "c2": dict(n=1_000_000, m=5, seed=0, obs_seed=0, desc="ForestPerformanceEval: 10^4 batches x 100 candidates x 5 prisms, early exit", scaling="weak"),
+    "c1": dict(n=15_571_728, m=1, seed=0, obs_seed=0, desc="PerformanceEval, repo defaults: the driver's mt19937(0) stream, 15 571 728 trials of which "
+               "10^7 pass CheckInputFeasibility(5,30,20,0.002) on the device (rqcd_set_input_filter), each vs its own sphere", scaling="weak"),
+    "c2": dict(n=1_000_000, m=5, seed=0, obs_seed=0, desc="ForestPerformanceEval, repo defaults: the driver's mt19937(0) stream, 10^4 batches x 100 "
+               "candidates x 5 prisms; per step CheckInputFeasibility with the per-batch generator object + early-exit check", scaling="weak"),
 }
 
 
@@ -146,35 +150,24 @@ def build_obstacles(name: str, W, abi, gen_coeffs):
 
 
 def host_inputs(name: str, W, base: int, n: int):
-    """Boundary conditions (19 x n) [+ spheres 4 x n for c1] for global indices [base, base+n)."""
+    """Boundary conditions (19 x n) [+ spheres 4 x n for c1] for indices [base, base+n) of the workload's input stream. c1 / c2
+    are the reference drivers' own mt19937(0) streams (workloads.c1_trials / c2_candidates; every rank replays the stream
+    from its start), c3 - c5 the counter-based generator (any index on either side)."""
     w = WORKLOADS[name]
     if name == "c2":
-        # ForestPerformanceEval's distributions (ForestPerformanceEval.cpp:77-102, 175-193), counter-based
-        u = W.synth_bc(w["seed"] + 100, base, n)  # U(-4,4) rows re-mapped below
-        unit = lambda r: (u[r] + 4.0) / 8.0  # noqa: E731
-        bc = np.zeros((19, n))
-        bc[0] = -2.5
-        batch = (np.arange(base, base + n) // 100).astype(np.int64)
-        ub = W.synth_bc(w["seed"] + 101, 0, int(batch.max()) + 1)
-        unit_b = lambda r: ((ub[r] + 4.0) / 8.0)[batch]  # noqa: E731
-        bc[3] = 2.0 + 6.0 * unit_b(3)
-        bc[4] = -2.0 + 4.0 * unit_b(4)
-        bc[5] = -2.0 + 4.0 * unit_b(5)
-        bc[6] = 4.0 + 6.0 * unit_b(6)
-        bc[7] = -2.0 + 4.0 * unit_b(7)
-        bc[8] = -2.0 + 4.0 * unit_b(8)
-        for r in (9, 10, 11):
-            bc[r] = -2.5 + 5.0 * unit(r)
-        bc[18] = 0.5 + 1.5 * unit(12)
-        return bc, None
-    bc = W.synth_bc(w["seed"], base, n)
-    sph = None
+        nb = (base + n + 99) // 100
+        return np.ascontiguousarray(W.c2_candidates(nb)[:, base:base + n]), None
     if name == "c1":
-        u = W.synth_bc(w["obs_seed"], base, n)
-        sph = np.empty((4, n))
-        sph[0:3] = u[3:6]                        # centre U(-4,4)^3
-        sph[3] = 0.1 + (u[6] + 4.0) / 8.0 * 1.4  # radius U[0.1,1.5]
-    return bc, sph
+        bc, sph = W.c1_trials(base + n)
+        return np.ascontiguousarray(bc[:, base:]), np.ascontiguousarray(sph[:, base:])
+    return W.synth_bc(w["seed"], base, n), None
+
+
+KNOWN = {  # the reference's checked-in results (data/PerformanceEval.txt:23-25, data/ForestPerfEval.txt:28-29)
+    "c1": {"traj_counts": [9_600_380, 399_612, 8]},
+    "c2": {"input_feasible": 639_533, "collision_free": 603_810},
+}
+FEAS_LIMITS = (5.0, 30.0, 20.0)  # fminAllowed, fmaxAllowed, wmaxAllowed of both drivers
 
 
 def cpu_checker():
@@ -184,16 +177,59 @@ def cpu_checker():
     return B.Oracle(), "port"
 
 
+def cpu_feasibility(impl, bc, threads, group=None):
+    """CheckInputFeasibility on the host cores: the checker's loop is single-threaded, so the range is cut into chunks (whole
+    groups when the candidates of a group share a generator object)."""
+    from concurrent.futures import ThreadPoolExecutor
+    n = bc.shape[1]
+    step = max(100, (n // (threads * 4) + 99) // 100 * 100)
+    cuts = list(range(0, n, step)) + [n]
+    def one(k):
+        lo, hi = cuts[k], cuts[k + 1]
+        return impl.input_feasibility(np.ascontiguousarray(bc[:, lo:hi]), group=None if group is None else group[lo:hi])
+    with ThreadPoolExecutor(threads) as ex:
+        return np.concatenate(list(ex.map(one, range(len(cuts) - 1))))
+
+
 def run_cpu(impl, name, obs, m, bc, sph, threads):
+    """One pass of the workload on the host cores, all threads: c1 = filter + pairwise check of the accepted trials, c2 = input
+    feasibility (per-batch object) + early-exit check of every candidate, else the all-pairs check."""
     from rapidquadcoptercollisiondetection_b200 import abi
     t0 = time.perf_counter()
     if name == "c1":
-        r = impl.generate_check_pairwise(bc, sph, MIN_T, nthreads=threads)
+        keep = cpu_feasibility(impl, bc, threads) == 0
+        r = impl.generate_check_pairwise(np.ascontiguousarray(bc[:, keep]), np.ascontiguousarray(sph[:, keep]), MIN_T, nthreads=threads)
+        r["accepted"] = keep
     else:
+        if name == "c2":
+            r0 = cpu_feasibility(impl, bc, threads, group=np.arange(bc.shape[1], dtype=np.int64) // 100)
         flags = abi.F_EARLY_EXIT if name == "c2" else 0
         r = impl.generate_check(bc, obs, m, MIN_T, flags=flags, matrix=False, nthreads=threads)
+        if name == "c2":
+            r["input_feasible"] = int((r0 == 0).sum())
     dt = time.perf_counter() - t0
     return r, dt
+
+
+def run_driver_binary(name):
+    """The reference's own driver, unmodified (oracle/_ref/PerformanceEval | ForestPerformanceEval, built by oracle/Makefile
+    from /root/reference/test/*.cpp): one thread, its own timers; returns the lines it prints."""
+    import re
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "PerformanceEval" if name == "c1" else "ForestPerformanceEval")
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        os.mkdir(os.path.join(d, "data"))
+        t0 = time.perf_counter()
+        out = subprocess.run([exe], cwd=d, capture_output=True, text=True, timeout=900).stdout
+        wall = time.perf_counter() - t0
+    res = {"binary": os.path.relpath(exe, ROOT), "wall_s": wall, "threads": 1}
+    for line in out.splitlines():
+        m = re.match(r"\s*(Average time[^=]*|Percent of[^=]*)=\s*([0-9.eE+-]+)", line)
+        if m:
+            res[m.group(1).strip()] = float(m.group(2))
+    return res
 
 
 def reference_arm(args):
@@ -223,6 +259,7 @@ def reference_arm(args):
     total = sum(times)
     value = pairs / total
     whole = n_s == w["n"]
+    driver = run_driver_binary(name) if name in ("c1", "c2") else None
     sample = (f"all {n_s} candidates" if whole else f"first {n_s} candidates") + f" of {name} x {len(specs) if name != 'c1' else 1} obstacles per step"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
@@ -235,6 +272,14 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if driver is not None:
+        line["reference_driver"] = driver
+    if name == "c1":
+        line["known_answer"] = {"expected": KNOWN["c1"], "got": r["summary"]["traj_counts"][:3],
+                                "match": whole and r["summary"]["traj_counts"][:3] == KNOWN["c1"]["traj_counts"]}
+    if name == "c2":
+        got = {"input_feasible": r.get("input_feasible"), "collision_free": r["summary"]["traj_counts"][0]}
+        line["known_answer"] = {"expected": KNOWN["c2"], "got": got, "match": whole and got == KNOWN["c2"]}
     emit(line)
 
 
@@ -320,13 +365,16 @@ class Resident:
         self.pairs_per_traj = 1 if name == "c1" else self.m
         self.flags = abi.F_EARLY_EXIT if name == "c2" else 0
         self.d_bc = torch.empty((abi.BC_ROWS, n), dtype=torch.float64, device=rig.dev)
-        self.d_sph = None
+        self.d_sph = self.d_feas = self.d_group = None
         self.bc_h = self.sph_h = None
         if name in ("c2", "c1"):
-            self.bc_h, self.sph_h = host_inputs(name, W, self.lo, n)
+            self.bc_h, self.sph_h = host_inputs(name, W, 0, n)  # every rank replays the driver's stream from its start
             self.d_bc.copy_(torch.from_numpy(self.bc_h))
+            self.d_feas = torch.empty(n, dtype=torch.uint8, device=rig.dev)
             if self.sph_h is not None:
                 self.d_sph = torch.from_numpy(self.sph_h).to(rig.dev)
+            if name == "c2":  # one generator object per batch of 100 (ForestPerformanceEval.cpp:177-209)
+                self.d_group = (torch.arange(n, dtype=torch.int64, device=rig.dev) // 100).contiguous()
         else:
             rig.ctx.synth_bc(w["seed"], self.lo, n, self.d_bc.data_ptr(), n)  # on the device from (seed, global index)
         self.d_verdict = torch.empty(n, dtype=torch.uint8, device=rig.dev)
@@ -335,12 +383,25 @@ class Resident:
         torch.cuda.synchronize(rig.dev)
 
     def enqueue(self, d_record: int):
-        """One step: the check launch (+ k_finalize) and the exchange (all-gather + merge), all on the stream, no host sync."""
+        """One step: the check launch (+ k_finalize) and the exchange (all-gather + merge), all on the stream, no host sync.
+        c1: the input filter runs inside the call (k_feas, then the check skips what it rejected); c2: the driver's
+        CheckInputFeasibility on every candidate (per-batch generator object) is a call of its own before the check."""
+        import ctypes as C
+
+        from rapidquadcoptercollisiondetection_b200 import abi
         ctx = self.rig.ctx
         if self.name == "c1":
             ctx.generate_check_pairwise_dev(self.d_bc.data_ptr(), self.n, self.d_sph.data_ptr(), self.n, self.n, MIN_T,
-                                            index_base=self.lo, d_verdict=self.d_verdict.data_ptr(), d_cost=self.d_cost.data_ptr())
+                                            index_base=self.lo, d_verdict=self.d_verdict.data_ptr(), d_cost=self.d_cost.data_ptr(),
+                                            d_input_feas=self.d_feas.data_ptr())
         else:
+            if self.name == "c2":
+                inp = abi.BcSoa(self.d_bc.data_ptr(), self.n, abi.GOAL_ALL, 0, 0, 0)
+                grav = (C.c_double * 3)(0.0, 0.0, -9.81)
+                st = ctx.lib.rqcd_check_input_feasibility(ctx.h, C.byref(inp), self.n, grav, *FEAS_LIMITS, MIN_T,
+                                                          C.c_void_p(self.d_group.data_ptr()), abi.F_DEVICE_PTRS,
+                                                          C.c_void_p(self.d_feas.data_ptr()))
+                assert st == abi.OK, st
             ctx.generate_check_dev(self.d_bc.data_ptr(), self.n, self.n, MIN_T, flags=self.flags, index_base=self.lo,
                                    d_verdict=self.d_verdict.data_ptr(), d_first=self.d_first.data_ptr(),
                                    d_cost=self.d_cost.data_ptr())
@@ -351,6 +412,8 @@ class Resident:
         device ring that is read once after the timed region."""
         rig, torch = self.rig, self.rig.torch
         ring = torch.zeros((max(steps, warmup), RECORD_WORDS), dtype=torch.int64, device=rig.dev)
+        if self.name == "c1":
+            rig.ctx.set_input_filter(fmin=FEAS_LIMITS[0], fmax=FEAS_LIMITS[1], wmax=FEAS_LIMITS[2], min_t=MIN_T)
         for k in range(warmup):
             self.enqueue(ring[k].data_ptr())
         rig.barrier()
@@ -646,22 +709,43 @@ def main():
         from oracle import binding as B
         orc = B.Oracle()
         n_s = max(1024, min(n, (1 << 22) // max(pairs_per_traj, 1)))
-        bc_s, sph_s = host_inputs(name, W, res.lo, n_s)
-        if name == "c1":
-            o = orc.generate_check_pairwise(bc_s, sph_s, MIN_T, nthreads=os.cpu_count() or 1, stats=True)
-        else:
-            o = orc.generate_check(bc_s, res.obs, m, MIN_T, flags=res.flags, matrix=False, nthreads=os.cpu_count() or 1, stats=True)
-        fpc = flops_per_check(o["stats"], pairs_per_traj)
-        # parity spot check of the resident results against the oracle sample (the checker, not the product)
+        stream_lo = 0 if name in ("c1", "c2") else res.lo
+        def sample(k):  # the first k candidates of this rank's input (c1 / c2: of the host copy of the driver's stream)
+            if res.bc_h is not None:
+                return (np.ascontiguousarray(res.bc_h[:, :k]), None if res.sph_h is None else np.ascontiguousarray(res.sph_h[:, :k]))
+            return host_inputs(name, W, stream_lo, k)
+        bc_s, sph_s = sample(n_s)
         got = res.d_verdict[:n_s].cpu().numpy()
-        parity = int((got != o["verdict"]).sum())
+        feas_flops = 0.0  # algorithmic flops of the input-feasibility stage per candidate (c1, c2), see f_rows_block
+        if name == "c1":
+            orc.feas_counters()
+            feas_s = orc.input_feasibility(bc_s)
+            sec, axis_it, full = orc.feas_counters()
+            feas_flops = 207.0 + (sec * 169.0 + axis_it * 71.0 + full * 8.0) / n_s
+            keep = feas_s == 0
+            o = orc.generate_check_pairwise(np.ascontiguousarray(bc_s[:, keep]), np.ascontiguousarray(sph_s[:, keep]), MIN_T,
+                                            nthreads=os.cpu_count() or 1, stats=True)
+            # parity of the sample: the filter's decisions, the verdicts of the accepted trials, 255 for the rejected ones
+            parity = int((res.d_feas[:n_s].cpu().numpy() != feas_s).sum() + (got[keep] != o["verdict"]).sum() + (got[~keep] != 255).sum())
+        else:
+            if name == "c2":
+                orc.feas_counters()
+                feas_s = orc.input_feasibility(bc_s, group=np.arange(n_s, dtype=np.int64) // 100)
+                sec, axis_it, full = orc.feas_counters()
+                feas_flops = 207.0 + (sec * 169.0 + axis_it * 71.0 + full * 8.0) / n_s
+            o = orc.generate_check(bc_s, res.obs, m, MIN_T, flags=res.flags, matrix=False, nthreads=os.cpu_count() or 1, stats=True)
+            # parity spot check of the resident results against the oracle sample (the checker, not the product)
+            parity = int((got != o["verdict"]).sum())
+            if name == "c2":
+                parity += int((res.d_feas[:n_s].cpu().numpy() != feas_s).sum())
+        fpc = flops_per_check(o["stats"], pairs_per_traj)
 
         cpu_baseline = None
         if not args.no_cpu_baseline:
             impl, kind = cpu_checker()
             threads = os.cpu_count() or 1
             n_c = max(1024, min(n, (1 << 25) // max(pairs_per_traj, 1)))  # ~1 s on 16 threads = ~16 core-seconds
-            bc_c, sph_c = host_inputs(name, W, res.lo, n_c)
+            bc_c, sph_c = sample(n_c)
             run_cpu(impl, name, res.obs, m, bc_c[:, :1024].copy(), None if sph_c is None else sph_c[:, :1024].copy(), threads)
             r, dt = run_cpu(impl, name, res.obs, m, bc_c, sph_c, threads)
             cpu_baseline = {"value": r["summary"]["pairs_checked"] / dt, "unit": UNIT, "cores": threads, "kind": kind,
@@ -670,7 +754,7 @@ def main():
         peaks = rig.ctx.measure_fp64_peak(200)
         kernel_s = (ms * 1e-3) / args.steps  # the check kernel dominates the step (k_finalize, memset, exchange ~ microseconds)
         pairs_per_launch = t["pairs_total"] / args.steps / world
-        achieved = fpc * pairs_per_launch / kernel_s / 1e12
+        achieved = (fpc * pairs_per_launch + feas_flops * n) / kernel_s / 1e12
         peak_tf = peaks["dmul_dadd_flops"] / 1e12
         measured = {}
         try:
@@ -706,6 +790,31 @@ def main():
             "trajectories_per_sec": t["trajectories_per_sec"],
             "summary": summary, "parity_mismatches_vs_oracle_sample": parity, "oracle_sample": n_s,
         }
+        if feas_flops:
+            roofline["flops_per_candidate_input_feasibility"] = feas_flops
+        # RQCD_F_FRAGILE on a sample: how many results are NOT pinned by the reference's arithmetic (grazing contact whose
+        # side is decided by the last bits of libm's acos / cos / pow, see include/rqcd.h); verdicts of unmarked pairs
+        # are the reference's on every conforming libm
+        n_f = min(n_s, 1 << 18)
+        bc_f = np.ascontiguousarray(bc_s[:, :n_f])
+        if name == "c1":
+            fr = rig.ctx.generate_check_pairwise(bc_f, np.ascontiguousarray(sph_s[:, :n_f]), MIN_T, fragile=True)
+            pairs_f, marked_pairs = int(fr["summary"]["pairs_checked"]), int(fr["fragile"].sum())
+        else:
+            fr = rig.ctx.generate_check(bc_f, MIN_T, flags=res.flags, matrix=not res.flags, fragile=True)
+            pairs_f = int(fr["summary"]["pairs_checked"])
+            marked_pairs = int((fr["fragile_matrix"] != 0).sum()) if "fragile_matrix" in fr else None
+        line["fragile"] = {"sample_candidates": n_f, "pairs_checked": pairs_f, "pairs_marked": marked_pairs,
+                           "trajectories_marked": int(fr["fragile"].sum()),
+                           "reasons": {int(k): int(v) for k, v in enumerate(rig.ctx.fragile_reasons()) if v}}
+        if name == "c1":
+            per_rank = [x // world for x in summary["traj_counts"][:3]]
+            line["known_answer"] = {"expected": KNOWN["c1"], "got": per_rank, "match": per_rank == KNOWN["c1"]["traj_counts"],
+                                    "source": "data/PerformanceEval.txt:23-25 (percentages x 10^7)"}
+        if name == "c2":
+            got_k = {"input_feasible": int((res.d_feas == 0).sum().item()), "collision_free": summary["traj_counts"][0] // world}
+            line["known_answer"] = {"expected": KNOWN["c2"], "got": got_k, "match": got_k == KNOWN["c2"],
+                                    "source": "data/ForestPerfEval.txt:28-29 (percentages x 10^6)"}
     del res
     rig.torch.cuda.empty_cache()
     if not args.no_extras and name != "c5":

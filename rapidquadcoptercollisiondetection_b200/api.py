@@ -341,10 +341,10 @@ class Context:
 
     def generate_check_pairwise_dev(self, d_bc: int, stride: int, d_spheres: int, sphere_stride: int, n: int,
                                     min_t: float, goal_mask=abi.GOAL_ALL, index_base=0, d_verdict=0, d_cost=0,
-                                    want_summary=False):
+                                    want_summary=False, d_input_feas=0):
         summ = abi.Summary()
         out = abi.Out(verdict=d_verdict or None, cost=d_cost or None,
-                      summary=C.pointer(summ) if want_summary else None)
+                      summary=C.pointer(summ) if want_summary else None, input_feasibility=d_input_feas or None)
         inp = abi.BcSoa(C.c_void_p(d_bc), stride, goal_mask, 0)
         st = self._chk(self.lib.rqcd_generate_check_pairwise(self.h, C.byref(inp), C.c_void_p(d_spheres), sphere_stride,
                                                              n, min_t, abi.F_DEVICE_PTRS, index_base, C.byref(out)),

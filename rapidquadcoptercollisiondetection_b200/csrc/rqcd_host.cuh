@@ -54,7 +54,8 @@ struct rqcd_ctx {
   rqcd_input_limits filter = {};
   int refill_min = 0;  // RQCD_REFILL_MIN override; 0 = chosen from the obstacle count
   int lockstep = -1;   // RQCD_LOCKSTEP override (0/1); -1 = chosen from the obstacle count
-  int pool = 1;        // RQCD_POOL (0/1): k_pool (staged sections, certified solver skip) for obstacle tables
+  int pool = 1;        // RQCD_POOL: 1 = k_pool (staged sections, certified solver skip) for moving tables and static ones of
+                       // 16+ obstacles, 2 = for every table, 0 = never (k_check)
   int th_solve = 32, th_plane = 24;  // RQCD_TH_SOLVE / RQCD_TH_PLANE: see CheckParams
   long long stream_timeout = 1ll << 32;  // RQCD_STREAM_TIMEOUT_CYCLES (~2 s): a streamed chunk that never arrives fails the call
   int n_probe_mag = 1, probe_log2[8] = {-50, 0, 0, 0, 0, 0, 0, 0};  // RQCD_F_FRAGILE probe magnitudes 2^k (RQCD_FRAGILE_LOG2)
