@@ -702,6 +702,21 @@ def main():
     t = res.time_steps(args.steps, args.warmup)
     ms, value, summary = t["ms"], t["value"], t["summary"]
     e2e = None if args.no_e2e else res.time_e2e(max(3, min(args.steps, 10)))
+    fast_fma = None
+    if not args.no_extras and name != "c1":
+        # RQCD_F_FAST_FMA (opt-in, NOT the reference's arithmetic): the same step with the kernels' FMA-contracted build,
+        # and how many verdicts / first hits of this rank's shard it changes
+        from rapidquadcoptercollisiondetection_b200 import abi
+        exact_v, exact_f = res.d_verdict.clone(), res.d_first.clone()
+        res.flags |= abi.F_FAST_FMA
+        tf = res.time_steps(max(3, args.steps // 3), 3, clocks=False)
+        res.flags &= ~abi.F_FAST_FMA
+        fast_fma = {"value": tf["value"], "unit": UNIT, "ms_per_step": tf["ms_per_step"], "speedup_over_exact": tf["value"] / value,
+                    "verdicts_changed": int((res.d_verdict != exact_v).sum().item()),
+                    "first_hits_changed": int((res.d_first != exact_f).sum().item()), "candidates_compared": res.n,
+                    "note": "opt-in flag; every headline number of this line is the exact (-fmad=false) build"}
+        res.d_verdict.copy_(exact_v)
+        res.d_first.copy_(exact_f)
 
     # ---- rank 0: CPU baseline on a bounded sample, flop model, roofline ---------------------------------------
     line = None
@@ -790,6 +805,8 @@ def main():
             "trajectories_per_sec": t["trajectories_per_sec"],
             "summary": summary, "parity_mismatches_vs_oracle_sample": parity, "oracle_sample": n_s,
         }
+        if fast_fma is not None:
+            line["fast_fma"] = fast_fma
         if feas_flops:
             roofline["flops_per_candidate_input_feasibility"] = feas_flops
         # RQCD_F_FRAGILE on a sample: how many results are NOT pinned by the reference's arithmetic (grazing contact whose

@@ -196,6 +196,13 @@ typedef struct rqcd_out {
  * default -50), RQCD_FRAGILE_MARGIN (4), RQCD_FRAGILE_FLOOR (8 ulps). rqcd_fragile_reasons says which decision it was. */
 #define RQCD_F_FRAGILE 0x4u
 
+/* Opt-in: run the check with the kernels' FMA-contracted build (the same sources compiled with -fmad=true instead of the
+ * default -fmad=false). About 7 % faster; NOT the reference's arithmetic: a contracted a*b+c rounds once where the
+ * reference's x86-64 build rounds twice, so coefficients and costs move in their last bits and a verdict can differ
+ * from the reference's (measured: 0 of 1.1e9 Monte Carlo pairs, tools/cmp_fmad.py; tests report the count). The
+ * input filter, RQCD_F_FRAGILE and every other entry point stay exact. */
+#define RQCD_F_FAST_FMA 0x8u
+
 #define RQCD_MAX_DEPTH 40       /* interval-stack entries per check */
 
 typedef struct rqcd_ctx rqcd_ctx;

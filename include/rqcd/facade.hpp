@@ -309,6 +309,55 @@ class Batch {
   int32_t m_ = 0;
 };
 
+// Several GPUs behind ONE C++ host (rqcd_group_*): candidates sharded by index over the devices, the obstacle set on every
+// device, each shard fed by its own host thread through the streaming pipeline; the shards' verdict counts and best
+// candidates are merged on the first device (peer-mapped slot table over NVLink + a merge kernel) -- the reduction the
+// drivers do on the host after every check (ForestPerformanceEval.cpp:216-230). Same results for every device count.
+class Group {
+ public:
+  explicit Group(const std::vector<int32_t>& devices) {
+    const int st = rqcd_group_create(&g_, devices.data(), (int32_t)devices.size());
+    if (st != RQCD_OK) throw Error(st, "rqcd_group_create");
+  }
+  ~Group() {
+    if (g_) rqcd_group_destroy(g_);
+  }
+  Group(const Group&) = delete;
+  Group& operator=(const Group&) = delete;
+  int32_t Size() const { return rqcd_group_size(g_); }
+  bool PeerSlots() const { return rqcd_group_peer_slots(g_) != 0; }
+
+  void SetObstacles(const std::vector<std::shared_ptr<CommonMath::ConvexObj>>& obstacles) {
+    std::vector<rqcd_obstacle> rec;
+    for (auto& o : obstacles) rec.push_back(o->Record());
+    check(rqcd_group_set_obstacles(g_, rec.data(), (int32_t)rec.size()));
+  }
+
+  // Batch::GenerateAndCheck over all devices: host buffers in, host buffers out, merged summary.
+  Batch::Result GenerateAndCheck(const double* bc, int64_t n, double minTimeSection, uint32_t goalMask = RQCD_GOAL_ALL,
+                                 bool earlyExit = false) {
+    Batch::Result r;
+    r.verdict.resize(n);
+    r.first_obstacle.resize(n);
+    r.cost.resize(n);
+    rqcd_bc_soa in = {bc, n, goalMask, 0};
+    rqcd_out out = {};
+    out.verdict = r.verdict.data();
+    out.first_obstacle = r.first_obstacle.data();
+    out.cost = r.cost.data();
+    out.summary = &r.summary;
+    check(rqcd_group_generate_check(g_, &in, n, minTimeSection, earlyExit ? RQCD_F_EARLY_EXIT : 0, &out), true);
+    return r;
+  }
+
+ private:
+  void check(int st, bool allow_depth_cap = false) const {
+    if (st == RQCD_OK || (allow_depth_cap && st == RQCD_ERR_DEPTH_CAP)) return;
+    throw Error(st, rqcd_group_last_error(g_));
+  }
+  rqcd_group* g_ = nullptr;
+};
+
 }  // namespace rqcd
 
 namespace rqcd {

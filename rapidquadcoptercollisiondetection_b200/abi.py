@@ -25,6 +25,7 @@ GOAL_ALL = 0x1FF
 F_DEVICE_PTRS = 0x1
 F_EARLY_EXIT = 0x2
 F_FRAGILE = 0x4
+F_FAST_FMA = 0x8
 MAX_DEPTH = 40
 COMM_ID_BYTES = 128
 

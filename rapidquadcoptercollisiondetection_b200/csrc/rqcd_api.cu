@@ -111,10 +111,30 @@ struct BlockList {
   }
 };
 
+}  // namespace
+
+// RQCD_F_FAST_FMA: the kernel files' second build (csrc/Makefile: -fmad=true, namespace rqcd_fma). Its parameter structs
+// are the same definitions under another namespace name, hence the same layout.
+namespace rqcd_fma {
+struct CheckParams;
+cudaError_t init_device_constants(cudaStream_t s);
+cudaError_t init_pool_constants(cudaStream_t s);
+cudaError_t launch_check(const CheckParams& p, int mode, bool moving, bool pairwise, int grid, cudaStream_t s);
+int check_max_blocks_per_sm(int mode, bool moving, bool pairwise, int m, size_t smem);
+cudaError_t check_prepare(int mode, bool moving, bool pairwise, int m, size_t smem);
+cudaError_t pool_prepare(int mode, bool moving, int threads, size_t smem);
+int pool_max_blocks_per_sm(int mode, bool moving, int threads, size_t smem);
+cudaError_t launch_pool(const CheckParams& p, int mode, bool moving, int threads, int grid, size_t smem, cudaStream_t s);
+}  // namespace rqcd_fma
+
+namespace {
+
 struct CheckCall : BlockList {
   int mode = MODE_BC;
   bool pairwise = false;
   CheckParams p = {};
+  bool fast_fma = false;  // RQCD_F_FAST_FMA
+  const uint8_t* filter_mask = nullptr;  // input filter: != 0 where the candidate was rejected (k_fragile skips those)
 };
 
 // ---- rqcd_bc_soa ------------------------------------------------------------------------------------------------------
@@ -184,8 +204,9 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
     p.th_solve = ctx->th_solve;
     p.th_plane = ctx->th_plane;
     const size_t smem = pool_smem_bytes(ctx->mp, ctx->stride, pool_t);
-    RQCD_CU(pool_prepare(cc.mode, moving, pool_t, smem));
-    int per_sm = pool_max_blocks_per_sm(cc.mode, moving, pool_t, smem);
+    RQCD_CU(cc.fast_fma ? rqcd_fma::pool_prepare(cc.mode, moving, pool_t, smem) : pool_prepare(cc.mode, moving, pool_t, smem));
+    int per_sm = cc.fast_fma ? rqcd_fma::pool_max_blocks_per_sm(cc.mode, moving, pool_t, smem)
+                             : pool_max_blocks_per_sm(cc.mode, moving, pool_t, smem);
     if (per_sm < 1) per_sm = 1;
     grid = (long long)sms * per_sm;
     const long long need = (p.n + pool_t - 1) / pool_t;
@@ -195,7 +216,11 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
     if (st != RQCD_OK) return st;
     p.partials = ctx->d_partials;
     RQCD_CU(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), ctx->stream));
-    RQCD_CU(launch_pool(p, cc.mode, moving, pool_t, (int)grid, smem, ctx->stream));
+    if (cc.fast_fma)
+      RQCD_CU(rqcd_fma::launch_pool(reinterpret_cast<const rqcd_fma::CheckParams&>(p), cc.mode, moving, pool_t, (int)grid, smem,
+                                    ctx->stream));
+    else
+      RQCD_CU(launch_pool(p, cc.mode, moving, pool_t, (int)grid, smem, ctx->stream));
     ctx->last_kernel = pool_kernel_name(moving);
   } else {
     // CTA lockstep or free-running warps, and the idle lanes per warp that trigger a work-queue fetch (in lockstep:
@@ -207,8 +232,10 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
     p.refill_min = ctx->refill_min > 0 ? ctx->refill_min : (cc.pairwise ? 8 : (p.m >= 128 ? 4 : (p.m >= 16 ? 6 : 4)));
     const size_t smem = check_smem_bytes(cc.pairwise ? 0 : ctx->mp, cc.pairwise ? 0 : ctx->stride, moving);
     if (smem > kMaxSmem) return RQCD_ERR_UNSUPPORTED;
-    RQCD_CU(check_prepare(cc.mode, moving, cc.pairwise, p.m, smem));
-    int per_sm = check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, p.m, smem);
+    RQCD_CU(cc.fast_fma ? rqcd_fma::check_prepare(cc.mode, moving, cc.pairwise, p.m, smem)
+                        : check_prepare(cc.mode, moving, cc.pairwise, p.m, smem));
+    int per_sm = cc.fast_fma ? rqcd_fma::check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, p.m, smem)
+                             : check_max_blocks_per_sm(cc.mode, moving, cc.pairwise, p.m, smem);
     if (per_sm < 1) per_sm = 1;
     grid = (long long)sms * per_sm;
     const long long need = (p.n + kThreads - 1) / kThreads;
@@ -218,7 +245,11 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
     if (st != RQCD_OK) return st;
     p.partials = ctx->d_partials;
     RQCD_CU(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), ctx->stream));
-    RQCD_CU(launch_check(p, cc.mode, moving, cc.pairwise, (int)grid, ctx->stream));
+    if (cc.fast_fma)
+      RQCD_CU(rqcd_fma::launch_check(reinterpret_cast<const rqcd_fma::CheckParams&>(p), cc.mode, moving, cc.pairwise, (int)grid,
+                                     ctx->stream));
+    else
+      RQCD_CU(launch_check(p, cc.mode, moving, cc.pairwise, (int)grid, ctx->stream));
     ctx->last_kernel = check_kernel_name(moving, cc.pairwise, p.m);
   }
   RQCD_CU(launch_finalize(ctx->d_partials, (int)grid, ctx->d_summary, ctx->stream));
@@ -329,10 +360,16 @@ int run_input_filter(rqcd_ctx* ctx, CheckCall& cc, const OutStage& o, long long 
   CheckParams q = cc.p;
   q.progress = nullptr;
   q.work_counter = ctx->d_counter;
+  // the accepted candidates as a dense list (any order): the check kernel then has no empty lanes for rejected ones
+  RQCD_CU(ensure(ctx->s_list, (size_t)n * 8 + 16));
+  unsigned long long* n_list = (unsigned long long*)ctx->s_list.p;
+  long long* list = (long long*)ctx->s_list.p + 2;
   RQCD_CU(launch_feasibility(q, L.gravity, L.fmin, L.fmax, L.wmax, L.min_time_section, nullptr, nullptr, d_feas, o.verdict,
-                             cc.pairwise ? nullptr : o.first, ctx->stream));
+                             cc.pairwise ? nullptr : o.first, list, n_list, ctx->stream));
   ctx->launches++;
-  cc.p.skip = d_feas;
+  cc.p.list = list;
+  cc.p.n_list = n_list;
+  cc.filter_mask = d_feas;
   return RQCD_OK;
 }
 
@@ -416,6 +453,9 @@ int run_fragile_probes(rqcd_ctx* ctx, CheckCall& cc, const OutStage& o, long lon
   CheckParams q = cc.p;
   q.progress = nullptr;  // the input is all there once the base launch has run
   q.stream_error = nullptr;
+  q.list = nullptr;  // one thread per pair of the whole range; pairs of candidates the input filter rejected are skipped
+  q.n_list = nullptr;
+  if (cc.filter_mask) q.skip = cc.filter_mask;
   const bool moving = ctx->any_moving;
   for (int k = 0; k < ctx->n_probe_mag; k++) {
     RQCD_CU(launch_fragile(q, cc.mode, moving && !cc.pairwise, cc.pairwise, std::ldexp(1.0, ctx->probe_log2[k]),
@@ -464,6 +504,7 @@ int finish_check(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, uint32_t fla
   }
   fill_params_out(cc.p, o);
   cc.p.early_exit = (flags & RQCD_F_EARLY_EXIT) ? 1 : 0;
+  cc.fast_fma = (flags & RQCD_F_FAST_FMA) != 0;
   int st;
   const bool filter = ctx->filter_on && cc.mode == MODE_BC && n > 0;
   if (filter) {
@@ -500,6 +541,9 @@ int finish_check(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, uint32_t fla
     }
   }
   cc.p.skip = nullptr;
+  cc.p.list = nullptr;
+  cc.p.n_list = nullptr;
+  cc.filter_mask = nullptr;
   if (!dev) RQCD_CU(cudaStreamSynchronize(ctx->stream));
   return sum_st;
 }
@@ -540,6 +584,8 @@ int rqcd_create(rqcd_ctx** out, int device) {
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_stream, (kMaxChunks + 1) * sizeof(unsigned long long));
   if (e == cudaSuccess) e = init_device_constants(ctx->own_stream);
   if (e == cudaSuccess) e = init_pool_constants(ctx->own_stream);
+  if (e == cudaSuccess) e = rqcd_fma::init_device_constants(ctx->own_stream);
+  if (e == cudaSuccess) e = rqcd_fma::init_pool_constants(ctx->own_stream);
   if (e != cudaSuccess) {
     rqcd_destroy(ctx);
     return RQCD_ERR_CUDA;
@@ -588,7 +634,7 @@ void rqcd_destroy(rqcd_ctx* ctx) {
   release(ctx->obs_blob);
   DevBuf* bufs[] = {&ctx->s_in,     &ctx->s_aux,   &ctx->s_verdict, &ctx->s_first,  &ctx->s_matrix, &ctx->s_cost,
                     &ctx->s_coeffs, &ctx->s_roots, &ctx->s_count,   &ctx->s_planes, &ctx->s_peaks,  &ctx->s_group,
-                    &ctx->s_fragile, &ctx->s_feas};
+                    &ctx->s_fragile, &ctx->s_feas, &ctx->s_list};
   for (DevBuf* b : bufs) release(*b);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->d_why) cudaFree(ctx->d_why);
@@ -994,7 +1040,7 @@ int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n
   if (group) RQCD_CU(ensure(ctx->s_peaks, (size_t)n * 8 * 6));
   p.work_counter = ctx->d_counter;
   RQCD_CU(launch_feasibility(p, gravity, fmin, fmax, wmax, min_time_section, dgroup, (double*)ctx->s_peaks.p, dres,
-                             nullptr, nullptr, ctx->stream));
+                             nullptr, nullptr, nullptr, nullptr, ctx->stream));
   ctx->launches += group ? 2 : 1;
   if (!dev) {
     RQCD_CU(cudaMemcpyAsync(result, dres, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1039,7 +1085,7 @@ int rqcd_plan_best(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n, const rqcd_p
   p.work_counter = ctx->d_counter;
   if (prm->check_input && n > 0) {
     RQCD_CU(launch_feasibility(p, prm->gravity, prm->fmin, prm->fmax, prm->wmax, prm->min_time_section, nullptr, nullptr,
-                               d_feas, nullptr, nullptr, s));
+                               d_feas, nullptr, nullptr, nullptr, nullptr, s));
     ctx->launches++;
   }
   // stage 2: plane boundaries

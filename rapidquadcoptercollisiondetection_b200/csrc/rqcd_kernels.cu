@@ -105,6 +105,8 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
 
   int n_have = 0;
   unsigned long long avail = 0;  // candidates known to have arrived (streaming input)
+  // with an accept list (input filter) the work items are positions of the list, else the candidates themselves
+  const long long n_work = p.n_list ? (long long)*p.n_list : p.n;
   for (;;) {
     // ---- CTA lockstep (p.lockstep, chosen per launch): one barrier per trip keeps the warps of a CTA in the same
     // part of the loop body, which is larger than the instruction cache, so an instruction line fetched from L2
@@ -123,7 +125,7 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
         unsigned long long b = 0;
         if (lane == 0) b = atomicAdd(p.work_counter, (unsigned long long)cnt);
         b = __shfl_sync(kFull, b, 0);
-        if (b + (unsigned long long)cnt >= (unsigned long long)p.n) exhausted = true;
+        if (b + (unsigned long long)cnt >= (unsigned long long)n_work) exhausted = true;
         bool arrived = true;
         if (p.progress) {  // streaming input: wait until the copy engine has delivered everything this warp took
           unsigned long long want = b + (unsigned long long)cnt;
@@ -132,9 +134,10 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
           if (!arrived) exhausted = true;
         }
         bool fresh = false;
-        const long long my_i = (long long)b + __popc(need & lt_mask);
+        const long long my_pos = (long long)b + __popc(need & lt_mask);
+        const long long my_i = (p.list && my_pos < n_work) ? p.list[my_pos] : my_pos;
         // planner: skip[i] != 0 was dropped by an earlier stage
-        const bool take = !have && my_i < p.n && arrived && !(p.skip && p.skip[my_i] != 0);
+        const bool take = !have && my_pos < n_work && arrived && !(p.skip && p.skip[my_i] != 0);
         double t0 = 0.0, t1 = 0.0, cost = 0.0;
         V3 x0 = v3(0, 0, 0), x1 = v3(0, 0, 0);
         double amax = 0.0;
@@ -148,9 +151,11 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
           const int my_rank = __popc(owners & lt_mask);
           const int q = lane / 3, ax = lane % 3;
           double tc[6] = {0, 0, 0, 0, 0, 0}, t_cost = 0.0, t_x0 = 0.0, t_x1 = 0.0, t_am = 0.0, t_tf = 0.0;
-          if (lane < 3 * kCoopOwners && q < n_own) {
-            const unsigned own = __fns(owners, 0, q + 1);
-            const long long i = (long long)b + __popc(need & ((1u << own) - 1u));
+          const bool helper = lane < 3 * kCoopOwners && q < n_own;
+          const unsigned own = helper ? __fns(owners, 0, q + 1) : 0u;
+          const long long own_i = __shfl_sync(kFull, my_i, (int)own);  // the q-th owner's candidate
+          if (helper) {
+            const long long i = own_i;
             const BcIndex x = bc_index(p, i);
             const double Tf = bc_at(p, 18, x);
             const double p0 = bc_at(p, 0 + ax, x), v0 = bc_at(p, 3 + ax, x), a0 = bc_at(p, 6 + ax, x);
@@ -379,7 +384,7 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
         if (p.verdict) p.verdict[idx] = (uint8_t)verdict;
         if (p.first_obstacle) p.first_obstacle[idx] = first;
         const double cost = RQCD_SLOT(SLOT_COST);
-        if (verdict == 0 && cost < bcost[tid]) {  // indices handed to one lane ascend, so ties keep the lowest
+        if (verdict == 0 && (cost < bcost[tid] || (cost == bcost[tid] && bidx[tid] >= 0 && p.index_base + idx < bidx[tid]))) {  // lowest index on ties
           bcost[tid] = cost;
           bidx[tid] = p.index_base + idx;
         }
@@ -944,7 +949,8 @@ __global__ void __launch_bounds__(128) k_feas_group_peaks(const CheckParams p, c
 constexpr int kFeasRows = 32;  // per queued candidate: 3 x (a0, alpha, beta, gamma) + 3 x (pk0, pk1, AxisHoist) + Tf + index
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const FeasArgs fa, const double* peaks, uint8_t* result,
-                                                    uint8_t* verdict, int* first, int refill) {
+                                                    uint8_t* verdict, int* first, int refill, long long* list,
+                                                    unsigned long long* n_list) {
   extern __shared__ __align__(16) double feas_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -1024,6 +1030,8 @@ __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const F
       hz[k].tmax = hoist[(6 * k + 4) * 128], hz[k].jm = hoist[(6 * k + 5) * 128];
     }
     int res = feas_frame_sel(ax, hz, fa.grav, fa.fmin, fa.fmax, fa.wmax, t1, t2, fa.min_t);
+    bool done_now = false;
+    const long long done_idx = idx;
     if (have) {
       if (res == FEAS_SPLIT) {
         if (sp >= kMaxDepth) {
@@ -1045,6 +1053,18 @@ __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const F
           if (first) first[idx] = -2;
         }
         have = false;
+        done_now = true;
+      }
+    }
+    // the input filter's accept list: the candidates decided InputFeasible in this trip, appended with one atomic per warp
+    if (list) {
+      const bool acc = done_now && res == RQCD_INPUT_FEASIBLE_;
+      const unsigned am = __ballot_sync(kFull, acc);
+      if (am) {
+        unsigned long long at = 0;
+        if (lane == __ffs(am) - 1) at = atomicAdd(n_list, (unsigned long long)__popc(am));
+        at = __shfl_sync(kFull, at, __ffs(am) - 1);
+        if (acc) list[at + __popc(am & lt_mask)] = done_idx;
       }
     }
   }
@@ -1289,7 +1309,7 @@ cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, 
 
 cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], double fmin, double fmax, double wmax,
                                double min_t, const long long* group, double* peaks, uint8_t* result, uint8_t* verdict, int* first,
-                               cudaStream_t s) {
+                               long long* list, unsigned long long* n_list, cudaStream_t s) {
   if (p.n <= 0) return cudaSuccess;
   FeasArgs fa;
   for (int k = 0; k < 3; k++) fa.grav[k] = grav[k];
@@ -1321,7 +1341,12 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const double* pk = group ? peaks : nullptr;
-  void* args[] = {(void*)&p, (void*)&fa, (void*)&pk, (void*)&result, (void*)&verdict, (void*)&first, (void*)&refill};
+  if (list) {
+    e = cudaMemsetAsync(n_list, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+  }
+  void* args[] = {(void*)&p, (void*)&fa, (void*)&pk, (void*)&result, (void*)&verdict, (void*)&first, (void*)&refill, (void*)&list,
+                  (void*)&n_list};
   return cudaLaunchKernel(fn, dim3(pgrid), dim3(128), args, smem, s);
 }
 

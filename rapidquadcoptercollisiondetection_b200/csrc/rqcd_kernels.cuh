@@ -75,6 +75,10 @@ struct CheckParams {
   long long stream_timeout;  // SM cycles a warp waits for a chunk before it fails the call
   // planner: candidates with skip[i] != 0 were rejected by an earlier stage and are not checked (nor counted)
   const uint8_t* skip;
+  // input filter: the candidates to check are list[0 .. *n_list) (indices into the launch's rows, any order; written by
+  // k_feas just before); null = all of [0, n)
+  const long long* list;
+  const unsigned long long* n_list;
 };
 
 // once per device, before any kernel that solves a cubic: the refined reciprocals of solveP3's constant divisors
@@ -115,7 +119,8 @@ cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, 
 // group may be null; peaks: scratch of 6*n doubles, needed when group is given
 cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], double fmin, double fmax, double wmax,
                                double min_t, const long long* group, double* peaks, uint8_t* result, uint8_t* verdict,
-                               int* first, cudaStream_t s);
+                               int* first, long long* list /* accepted candidates, may be null */, unsigned long long* n_list,
+                               cudaStream_t s);
 // planner glue (rqcd_plan_best): stage codes, see rqcd_plan_stage in rqcd.h
 cudaError_t launch_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas, const uint8_t* plane_hit,
                              uint8_t* stage, cudaStream_t s);

@@ -181,20 +181,23 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
   bool exhausted = false;
   const bool early = p.early_exit != 0;
 
+  // with an accept list (input filter) the work items are positions of the list, else the candidates themselves
+  const long long n_work = p.n_list ? (long long)*p.n_list : p.n;
   while (!exhausted) {
     // ---- a batch of 32 candidates
     unsigned long long b = 0;
     if (lane == 0) b = atomicAdd(p.work_counter, 32ull);
     b = __shfl_sync(kFull, b, 0);
-    if (b >= (unsigned long long)p.n) break;
-    if (b + 32ull >= (unsigned long long)p.n) exhausted = true;
+    if (b >= (unsigned long long)n_work) break;
+    if (b + 32ull >= (unsigned long long)n_work) exhausted = true;
     if (p.progress) {  // streaming input: wait until the copy engine has delivered the whole batch
       unsigned long long want = b + 32ull;
       if (want > (unsigned long long)p.n) want = (unsigned long long)p.n;
       if (!wait_for_input(p, want, avail, lane)) break;
     }
-    const long long idx = (long long)b + lane;
-    const bool have = idx < p.n && !(p.skip && p.skip[idx] != 0);  // planner: dropped by an earlier stage
+    const long long pos = (long long)b + lane;
+    const long long idx = (p.list && pos < n_work) ? p.list[pos] : pos;
+    const bool have = pos < n_work && !(p.skip && p.skip[idx] != 0);  // planner: dropped by an earlier stage
     double t0 = 0.0, t1 = 0.0, cost = 0.0;
     V3 x0 = v3(0, 0, 0), x1 = v3(0, 0, 0), xm0 = v3(0, 0, 0);
     double hull_r = __longlong_as_double(0x7ff0000000000000ll);  // bound of |X(t) - X(mid)| on the window; +inf: no cull
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
     if (have) {
       if (p.verdict) p.verdict[idx] = (uint8_t)verdict;
       if (p.first_obstacle) p.first_obstacle[idx] = first;
-      if (verdict == 0 && cost < bcost[tid]) {  // indices handed to one lane ascend, so ties keep the lowest
+      if (verdict == 0 && (cost < bcost[tid] || (cost == bcost[tid] && bidx[tid] >= 0 && p.index_base + idx < bidx[tid]))) {  // lowest index on ties
         bcost[tid] = cost;
         bidx[tid] = p.index_base + idx;
       }

@@ -76,6 +76,32 @@ int main(int argc, char** argv) {
            (unsigned long long)got.summary.pairs_checked, (unsigned long long)got.summary.traj_counts[0],
            (long long)got.summary.best_index, bad);
 
+    // ---- the same call from a multi-GPU C++ host (rqcd::Group = rqcd_group_*): every visible GPU, or two shards on the
+    // one GPU there is; verdicts, costs and the MERGED summary (counts, best candidate) must equal the single-context call
+    {
+      int ndev = 0;
+      {
+        rqcd_ctx* probe = nullptr;
+        while (ndev < 8 && rqcd_create(&probe, ndev) == RQCD_OK) {
+          rqcd_destroy(probe);
+          ndev++;
+        }
+      }
+      std::vector<int32_t> devs;
+      if (ndev >= 2) for (int d = 0; d < ndev; d++) devs.push_back(d);
+      else devs = {0, 0};
+      rqcd::Group group(devs);
+      group.SetObstacles(obstacles);
+      rqcd::Batch::Result gg = group.GenerateAndCheck(bc.data(), n, minT, RQCD_GOAL_ALL, /*earlyExit=*/true);
+      int badGroup = 0;
+      for (int64_t i = 0; i < n; i++)
+        if (gg.verdict[i] != got.verdict[i] || gg.first_obstacle[i] != got.first_obstacle[i] || gg.cost[i] != got.cost[i]) badGroup++;
+      if (memcmp(&gg.summary, &got.summary, sizeof(rqcd_summary)) != 0) badGroup++;
+      printf("group of %d shards on %d device(s) (%s slots): mismatches %d\n", group.Size(), ndev >= 2 ? ndev : 1,
+             group.PeerSlots() ? "peer-mapped" : "host-mapped", badGroup);
+      bad += badGroup;
+    }
+
     // ---- single objects: the reference's loop body UNCHANGED (ForestPerformanceEval.cpp:175-225) for the first two
     // batches -- one generator object per batch, SetGoalPosition / Generate / CheckInputFeasibility / GetTrajectory /
     // CollisionCheck per candidate. The per-object acceleration peak-time cache makes later candidates of a batch depend

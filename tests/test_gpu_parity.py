@@ -573,3 +573,34 @@ def test_input_filter_reproduces_performance_eval(ctx, oracle):
     np.testing.assert_array_equal(f["first_obstacle"][k2], o2["first_obstacle"])
     assert (f["verdict"][~k2] == abi.NOT_CHECKED).all() and (f["first_obstacle"][~k2] == -2).all()
     assert f["summary"]["traj_counts"] == o2["summary"]["traj_counts"]
+
+
+def test_fast_fma_flag_is_opt_in_and_close(ctx, oracle):
+    """RQCD_F_FAST_FMA runs the kernels' FMA-contracted build: costs and coefficients within 1e-12 of the exact build, verdicts
+    equal on (nearly) every Monte Carlo pair -- the count is printed, a handful in 1e6 would be legitimate -- while the
+    default call stays bit-exact against the oracle."""
+    specs = W.static_obstacles(2, 32, 32)
+    obs = abi.make_obstacles(specs)
+    bc = W.synth_bc(1, 0, 1 << 15)
+    ctx.set_obstacles(obs, len(specs))
+    exact = ctx.generate_check(bc, MIN_T)
+    fma = ctx.generate_check(bc, MIN_T, flags=abi.F_FAST_FMA)
+    o = oracle.generate_check(bc, obs, len(specs), MIN_T, nthreads=8)
+    np.testing.assert_array_equal(exact["verdict_matrix"], o["verdict_matrix"])
+    changed = int((fma["verdict_matrix"] != exact["verdict_matrix"]).sum())
+    print(f"fast fma: {changed} of {exact['verdict_matrix'].size} pair verdicts changed")
+    assert changed <= 1e-5 * exact["verdict_matrix"].size
+    assert_close(fma["cost"], exact["cost"], tol=1e-12, what="cost, contracted build")
+    # the other shapes run too: pairwise (k_check), early exit over a short table (k_check), moving table (k_pool)
+    u = W.synth_bc(8, 0, 1 << 14)
+    sph = np.empty((4, 1 << 14))
+    sph[0:3] = u[3:6]
+    sph[3] = 0.1 + (u[6] + 4.0) / 8.0 * 1.4
+    b14 = np.ascontiguousarray(bc[:, :1 << 14])
+    pe = ctx.generate_check_pairwise(b14, sph, MIN_T)
+    ctx.set_obstacles(abi.make_obstacles(W.forest_obstacles()), 5)
+    c2 = W.c2_candidates(100)
+    fe = ctx.generate_check(c2, MIN_T, flags=abi.F_EARLY_EXIT)
+    ff = ctx.generate_check(c2, MIN_T, flags=abi.F_EARLY_EXIT | abi.F_FAST_FMA)
+    assert int((fe["verdict"] != ff["verdict"]).sum()) <= 2
+    assert pe["summary"]["pairs_checked"] == 1 << 14
