@@ -63,7 +63,9 @@ typedef enum rqcd_input_feasibility {
   RQCD_INPUT_INDETERMINABLE = 1,
   RQCD_INPUT_INFEASIBLE_THRUST_HIGH = 2,
   RQCD_INPUT_INFEASIBLE_THRUST_LOW = 3,
-  RQCD_INPUT_INFEASIBLE_RATES = 4
+  RQCD_INPUT_INFEASIBLE_RATES = 4,
+  RQCD_INPUT_DEPTH_CAP = 5 /* not a reference value: more than RQCD_MAX_DEPTH pending second halves (needs Tf / minTimeSection
+                              > 2^40); the reference would recurse on. Never silent: reported instead of folded into 1 */
 } rqcd_input_feasibility;
 
 /* ---- obstacles -----------------------------------------------------------
@@ -191,8 +193,8 @@ typedef struct rqcd_out {
  * before its first hit has such a decision; with a verdict_matrix, bit 7 of an entry marks the pair (the verdict stays in
  * bits 0..1). Verdicts are never changed. An unmarked verdict is the reference's on every conforming libm (tests: every
  * difference from the CPU reference on adversarial grazing populations is marked, with zero tolerance); a marked one
- * is a coin toss in the reference too. Monte Carlo batches: ~5e-6 of the pairs. Cost: about the time of the check again
- * per 2e8 pairs (one thread per pair, compiler divisions). Tunables, read at rqcd_create: RQCD_FRAGILE_LOG2 (magnitudes,
+ * is a coin toss in the reference too. Monte Carlo batches: ~5e-6 of the pairs. Cost: a diagnostic, not a hot path --
+ * one thread per pair, nine copies, the compiler's divisions: ~6e7 pairs/s (the check itself does 2e10). Tunables, read at rqcd_create: RQCD_FRAGILE_LOG2 (magnitudes,
  * default -50), RQCD_FRAGILE_MARGIN (4), RQCD_FRAGILE_FLOOR (8 ulps). rqcd_fragile_reasons says which decision it was. */
 #define RQCD_F_FRAGILE 0x4u
 

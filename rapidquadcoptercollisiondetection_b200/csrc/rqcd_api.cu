@@ -181,6 +181,18 @@ void stage_bc(CheckParams& p, BlockList& bl, const rqcd_bc_soa* in, long long n,
   p.group_size = G;
 }
 
+// Which kernel a check call runs on: the CTA size of k_pool (staged sections) for obstacle tables that fit beside the
+// trajectory rows, 0 = k_check (the pairwise shape, empty and oversized tables, short static tables).
+int pool_threads_for(const rqcd_ctx* ctx, bool pairwise) {
+  const bool moving = !pairwise && ctx->any_moving;
+  // short static tables (the Forest's five trees: 4.4 executed pairs per candidate with early exit) spend their time
+  // building candidates, not in sections: k_check's lane-owns-trajectory loop is 30 % faster there (5.2e9 vs 3.9e9 checks/s)
+  const bool short_static = !moving && ctx->m < kEndBitsMinObstacles && ctx->pool < 2;
+  if (ctx->pool && !short_static && !pairwise && ctx->m >= 1 && ctx->m < 65536)
+    return pool_threads(ctx->mp, ctx->stride, ctx->prop.sharedMemPerMultiprocessor, kMaxSmem);
+  return 0;
+}
+
 int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   const bool moving = !cc.pairwise && ctx->any_moving;
   CheckParams& p = cc.p;
@@ -193,12 +205,7 @@ int run_check(rqcd_ctx* ctx, CheckCall& cc) {
   const int sms = ctx->prop.multiProcessorCount;
   // ---- which kernel: obstacle tables go to k_pool (staged sections with the certified solver skip) when the table
   // fits beside the trajectory rows; the pairwise shape, empty tables and oversized tables go to k_check
-  int pool_t = 0;
-  // short static tables (the Forest's five trees: 4.4 executed pairs per candidate with early exit) spend their time
-  // building candidates, not in sections: k_check's lane-owns-trajectory loop is 30 % faster there (5.2e9 vs 3.9e9 checks/s)
-  const bool short_static = !moving && p.m < kEndBitsMinObstacles && ctx->pool < 2;
-  if (ctx->pool && !short_static && !cc.pairwise && p.m >= 1 && p.m < 65536)
-    pool_t = pool_threads(ctx->mp, ctx->stride, ctx->prop.sharedMemPerMultiprocessor, kMaxSmem);
+  const int pool_t = pool_threads_for(ctx, cc.pairwise);
   long long grid;
   if (pool_t > 0) {
     p.th_solve = ctx->th_solve;
@@ -294,24 +301,55 @@ struct OutStage {  // device-side output pointers + what must be copied back
   double* cost = nullptr;
   double* coeffs = nullptr;
   long long coeff_stride = 0;
+  // the per-candidate results go STRAIGHT to the caller's page-locked host buffer (the kernel stores through its device
+  // alias: coalesced 32 / 128 / 256-byte posted writes over PCIe that overlap the rest of the kernel) instead of to a
+  // staging buffer that is copied back after the kernel
+  bool direct_verdict = false, direct_first = false, direct_cost = false;
 };
 
-int stage_outputs(rqcd_ctx* ctx, const rqcd_out* out, long long n, int m, bool want_cost_coeffs, OutStage& o) {
+// The device alias of a page-locked, mapped host buffer (cudaHostAlloc / cudaHostRegister under unified addressing), else null.
+template <class T>
+T* mapped_alias(T* host) {
+  cudaPointerAttributes at;
+  if (!host || cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return (at.type == cudaMemoryTypeHost && at.devicePointer) ? (T*)at.devicePointer : nullptr;
+}
+
+int stage_outputs(rqcd_ctx* ctx, const rqcd_out* out, long long n, int m, bool want_cost_coeffs, OutStage& o, bool allow_direct) {
+  const bool direct = allow_direct && ctx->direct_out;
   if (out->verdict) {
-    RQCD_CU(ensure(ctx->s_verdict, (size_t)n));
-    o.verdict = (uint8_t*)ctx->s_verdict.p;
+    uint8_t* alias = direct ? mapped_alias(out->verdict) : nullptr;
+    if (alias) {
+      o.verdict = alias, o.direct_verdict = true;
+    } else {
+      RQCD_CU(ensure(ctx->s_verdict, (size_t)n));
+      o.verdict = (uint8_t*)ctx->s_verdict.p;
+    }
   }
   if (out->first_obstacle) {
-    RQCD_CU(ensure(ctx->s_first, (size_t)n * 4));
-    o.first = (int*)ctx->s_first.p;
+    int* alias = direct ? mapped_alias(out->first_obstacle) : nullptr;
+    if (alias) {
+      o.first = alias, o.direct_first = true;
+    } else {
+      RQCD_CU(ensure(ctx->s_first, (size_t)n * 4));
+      o.first = (int*)ctx->s_first.p;
+    }
   }
   if (out->verdict_matrix) {
     RQCD_CU(ensure(ctx->s_matrix, (size_t)n * (size_t)(m > 0 ? m : 1)));
     o.matrix = (uint8_t*)ctx->s_matrix.p;
   }
   if (want_cost_coeffs && out->cost) {
-    RQCD_CU(ensure(ctx->s_cost, (size_t)n * 8));
-    o.cost = (double*)ctx->s_cost.p;
+    double* alias = direct ? mapped_alias(out->cost) : nullptr;
+    if (alias) {
+      o.cost = alias, o.direct_cost = true;
+    } else {
+      RQCD_CU(ensure(ctx->s_cost, (size_t)n * 8));
+      o.cost = (double*)ctx->s_cost.p;
+    }
   }
   if (want_cost_coeffs && out->coeffs) {
     RQCD_CU(ensure(ctx->s_coeffs, (size_t)n * 8 * RQCD_COEFF_ROWS));
@@ -341,12 +379,13 @@ int validate_out(const rqcd_out* out, uint32_t flags, long long n) {
 int outputs_d2h(rqcd_ctx* ctx, const rqcd_out* out, long long n, int m, const OutStage& o) {
   cudaStream_t cs = ctx->stream;
   if (n > 0) {
-    if (o.verdict && out->verdict) RQCD_CU(cudaMemcpyAsync(out->verdict, o.verdict, (size_t)n, cudaMemcpyDeviceToHost, cs));
-    if (o.first && out->first_obstacle)
+    if (o.verdict && out->verdict && !o.direct_verdict)
+      RQCD_CU(cudaMemcpyAsync(out->verdict, o.verdict, (size_t)n, cudaMemcpyDeviceToHost, cs));
+    if (o.first && out->first_obstacle && !o.direct_first)
       RQCD_CU(cudaMemcpyAsync(out->first_obstacle, o.first, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
     if (o.matrix && m > 0)
       RQCD_CU(cudaMemcpyAsync(out->verdict_matrix, o.matrix, (size_t)n * (size_t)m, cudaMemcpyDeviceToHost, cs));
-    if (o.cost) RQCD_CU(cudaMemcpyAsync(out->cost, o.cost, (size_t)n * 8, cudaMemcpyDeviceToHost, cs));
+    if (o.cost && !o.direct_cost) RQCD_CU(cudaMemcpyAsync(out->cost, o.cost, (size_t)n * 8, cudaMemcpyDeviceToHost, cs));
     if (o.coeffs) RQCD_CU(rows_d2h(out->coeffs, out->coeff_stride, o.coeffs, n, RQCD_COEFF_ROWS, cs));
   }
   return RQCD_OK;
@@ -482,7 +521,11 @@ int finish_check(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, uint32_t fla
       o.coeff_stride = out->coeff_stride;
     }
   } else {
-    int st = stage_outputs(ctx, out, n, m, want_cost_coeffs, o);
+    // Direct result stores only where the kernel writes a whole batch of 32 candidates at once (k_pool: 32 / 128 / 256-byte
+    // coalesced stores); k_check's and the input filter's lanes finish one by one, which would be single small PCIe writes.
+    // The fragile probes read the verdicts and first hits back on the device: staged then.
+    const bool batch_stores = pool_threads_for(ctx, cc.pairwise) > 0 && !(ctx->filter_on && cc.mode == MODE_BC);
+    int st = stage_outputs(ctx, out, n, m, want_cost_coeffs, o, /*allow_direct=*/!fragile && batch_stores);
     if (st != RQCD_OK) return st;
   }
   uint8_t* d_fragile = nullptr;
@@ -615,6 +658,8 @@ int rqcd_create(rqcd_ctx** out, int device) {
     }
     if (ctx->n_probe_mag == 0) ctx->n_probe_mag = 1, ctx->probe_log2[0] = -50;
   }
+  const char* dz = getenv("RQCD_DIRECT_OUT");
+  if (dz && (dz[0] == '0' || dz[0] == '1') && dz[1] == 0) ctx->direct_out = dz[0] == '1';
   const char* fm = getenv("RQCD_FRAGILE_MARGIN");
   if (fm && atof(fm) >= 1.0) ctx->probe_margin = atof(fm);
   const char* ff = getenv("RQCD_FRAGILE_FLOOR");

@@ -1035,7 +1035,7 @@ __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const F
     if (have) {
       if (res == FEAS_SPLIT) {
         if (sp >= kMaxDepth) {
-          res = RQCD_INPUT_INDETERMINABLE_;
+          res = 5;  // RQCD_INPUT_DEPTH_CAP
         } else {
           const double th = (t1 + t2) / 2;
           stack[sp++] = make_double2(th, t2);

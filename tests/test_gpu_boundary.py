@@ -256,3 +256,57 @@ def test_exchange_without_host_round_trip(ctx, oracle):
         assert list(rec[step, 4:8]) == o["summary"]["pair_counts"]
         assert int(rec[step, 10]) == o["summary"]["best_index"]
     assert merge_summaries([merged]) == merged
+
+
+@pytest.mark.parametrize("shape", ["table", "pairwise", "early_exit"])
+def test_page_locked_output_buffers_are_written_directly(shape, oracle):
+    """Host-pointer calls whose verdict / first-hit / cost buffers are page-locked get their results by direct stores of the
+    kernel (no staging copy after the launch); pageable buffers are staged. Both must hold the same bytes, and the
+    oracle's; RQCD_DIRECT_OUT=0 switches the direct path off."""
+    import torch
+    n = 77_777
+    bc = W.synth_bc(31, 0, n)
+    keep_in, bc_pin = _pinned(bc)
+    specs = W.static_obstacles(33, 10, 10) if shape != "early_exit" else W.forest_obstacles()
+    obs = abi.make_obstacles(specs)
+    u = W.synth_bc(32, 0, n)
+    sph = np.empty((4, n))
+    sph[0:3] = u[3:6]
+    sph[3] = 0.1 + (u[6] + 4.0) / 8.0 * 1.4
+    flags = abi.F_EARLY_EXIT if shape == "early_exit" else 0
+
+    def call(ctx, pinned_out):
+        mk = (lambda dt: torch.empty(n, dtype=dt).pin_memory().numpy()) if pinned_out else (lambda dt: torch.empty(n, dtype=dt).numpy())
+        v, f, c = mk(torch.uint8), mk(torch.int32), mk(torch.float64)
+        v[:], f[:], c[:] = 77, -7, -1.0
+        summ = abi.Summary()
+        inp = abi.BcSoa(bc_pin.ctypes.data, n, abi.GOAL_ALL, 0, 0, 0)
+        if shape == "pairwise":
+            out = abi.Out(verdict=v.ctypes.data, cost=c.ctypes.data, summary=C.pointer(summ))
+            st = ctx.lib.rqcd_generate_check_pairwise(ctx.h, C.byref(inp), sph.ctypes.data, n, n, MIN_T, 0, 0, C.byref(out))
+        else:
+            out = abi.Out(verdict=v.ctypes.data, first_obstacle=f.ctypes.data, cost=c.ctypes.data, summary=C.pointer(summ))
+            st = ctx.lib.rqcd_generate_check(ctx.h, C.byref(inp), n, MIN_T, flags, 0, C.byref(out))
+        assert st == abi.OK
+        return v.copy(), f.copy(), c.copy(), summ.as_dict()
+
+    with Context(0) as ctx:
+        if shape != "pairwise":
+            ctx.set_obstacles(obs, len(specs))
+        direct = call(ctx, True)
+        staged = call(ctx, False)
+    with _fresh_ctx({"RQCD_DIRECT_OUT": 0}) as c0:
+        if shape != "pairwise":
+            c0.set_obstacles(obs, len(specs))
+        off = call(c0, True)
+    if shape == "pairwise":
+        o = oracle.generate_check_pairwise(bc, sph, MIN_T, nthreads=8)
+    else:
+        o = oracle.generate_check(bc, obs, len(specs), MIN_T, flags=flags, matrix=False, nthreads=8)
+    for got in (direct, staged, off):
+        np.testing.assert_array_equal(got[0], o["verdict"])
+        if shape != "pairwise":
+            np.testing.assert_array_equal(got[1], o["first_obstacle"])
+        assert_close(got[2], o["cost"], what="cost")
+        assert got[3]["traj_counts"] == o["summary"]["traj_counts"]
+    np.testing.assert_array_equal(direct[2], staged[2])

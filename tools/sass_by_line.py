@@ -17,13 +17,14 @@ def main():
     sub = sys.argv[3] if len(sys.argv) > 3 else "k_checkILi0ELb0ELb0"
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-    cubin = [f for f in os.listdir(tmp) if f.startswith("rqcd_kernels.") and f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    dis = []  # every cubin of the library (one per kernel file and build); the kernel is found by its name
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
     # instructions of the kernel, each with the innermost (file, line)
     insts, cur, inside = [], ("?", 0), False
     for ln in dis:
         if ln.startswith(".text.") and ln.endswith(":"):
-            inside = sub in ln
+            inside = sub in ln and "$" not in ln and not insts  # the first matching kernel, not its out-of-line helpers
             continue
         if not inside:
             continue
