@@ -188,8 +188,13 @@ int pool_threads_for(const rqcd_ctx* ctx, bool pairwise) {
   // short static tables (the Forest's five trees: 4.4 executed pairs per candidate with early exit) spend their time
   // building candidates, not in sections: k_check's lane-owns-trajectory loop is 30 % faster there (5.2e9 vs 3.9e9 checks/s)
   const bool short_static = !moving && ctx->m < kEndBitsMinObstacles && ctx->pool < 2;
-  if (ctx->pool && !short_static && !pairwise && ctx->m >= 1 && ctx->m < 65536)
-    return pool_threads(ctx->mp, ctx->stride, ctx->prop.sharedMemPerMultiprocessor, kMaxSmem);
+  if (ctx->pool && !short_static && !pairwise && ctx->m >= 1 && ctx->m < 65536) {
+    const int t = pool_threads(ctx->mp, ctx->stride, ctx->prop.sharedMemPerMultiprocessor, kMaxSmem);
+    // RQCD_POOL_THREADS (256 / 384 / 512): the CTA size by hand, when that size fits
+    if (t > 0 && ctx->pool_threads_override > 0 && pool_smem_bytes(ctx->mp, ctx->stride, ctx->pool_threads_override) <= kMaxSmem)
+      return ctx->pool_threads_override;
+    return t;
+  }
   return 0;
 }
 
@@ -658,6 +663,8 @@ int rqcd_create(rqcd_ctx** out, int device) {
     }
     if (ctx->n_probe_mag == 0) ctx->n_probe_mag = 1, ctx->probe_log2[0] = -50;
   }
+  const char* pt = getenv("RQCD_POOL_THREADS");
+  if (pt && (atoi(pt) == 256 || atoi(pt) == 384 || atoi(pt) == 512)) ctx->pool_threads_override = atoi(pt);
   const char* dz = getenv("RQCD_DIRECT_OUT");
   if (dz && (dz[0] == '0' || dz[0] == '1') && dz[1] == 0) ctx->direct_out = dz[0] == '1';
   const char* fm = getenv("RQCD_FRAGILE_MARGIN");

@@ -50,6 +50,7 @@ struct rqcd_ctx {
   bool merged_valid = false;
   // staging for host-pointer calls
   rqcd::DevBuf s_in, s_aux, s_verdict, s_first, s_matrix, s_cost, s_coeffs, s_roots, s_count, s_planes, s_peaks, s_group, s_fragile, s_feas, s_list;
+  int pool_threads_override = 0;  // RQCD_POOL_THREADS
   bool direct_out = true;  // RQCD_DIRECT_OUT: results of host-pointer calls stored straight into page-locked output buffers
   bool filter_on = false;  // rqcd_set_input_filter
   rqcd_input_limits filter = {};
