@@ -1089,7 +1089,7 @@ int rqcd_check_input_feasibility(rqcd_ctx* ctx, const rqcd_bc_soa* in, int64_t n
     RQCD_CU(ensure(ctx->s_verdict, (size_t)n));
     dres = (uint8_t*)ctx->s_verdict.p;
   }
-  if (group) RQCD_CU(ensure(ctx->s_peaks, (size_t)n * 8 * 6));
+  if (group) RQCD_CU(ensure(ctx->s_peaks, (size_t)n * 8 * 6 + (size_t)n));  // + the anchor bytes, see k_feas_group_peaks
   p.work_counter = ctx->d_counter;
   RQCD_CU(launch_feasibility(p, gravity, fmin, fmax, wmax, min_time_section, dgroup, (double*)ctx->s_peaks.p, dres,
                              nullptr, nullptr, nullptr, nullptr, ctx->stream));

@@ -435,16 +435,19 @@ __global__ void RQCD_CHECK_BOUNDS k_check(const CheckParams p) {
 }
 
 
+// The CTA partials of a check launch -> the launch's summary. One block; counts by warp shuffles (shared-memory atomics on
+// eight 64-bit words from 256 threads serialise: the first version of this kernel took 40 us for 296 partials), the best
+// candidate by the same rule everywhere (lowest cost, lowest index on ties), partials visited in block order.
 __global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int nparts, DevSummary* out) {
-  __shared__ unsigned long long cnt[8];
-  __shared__ double scost[256];
-  __shared__ long long sidx[256];
-  const int tid = threadIdx.x;
-  if (tid < 8) cnt[tid] = 0ull;
+  __shared__ unsigned long long wsum[8][8];
+  __shared__ double wcost[8];
+  __shared__ long long widx[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double bc = __longlong_as_double(0x7ff0000000000000ll);
   long long bi = -1;
   unsigned long long loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int j = tid; j < nparts; j += blockDim.x) {
+#pragma unroll
     for (int v = 0; v < 4; v++) {
       loc[v] += parts[j].traj[v];
       loc[4 + v] += parts[j].pair[v];
@@ -454,18 +457,33 @@ __global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int
       bi = parts[j].best_index;
     }
   }
-  scost[tid] = bc;
-  sidx[tid] = bi;
-  __syncthreads();
-  for (int v = 0; v < 8; v++)
-    if (loc[v]) atomicAdd(&cnt[v], loc[v]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int v = 0; v < 8; v++) loc[v] += __shfl_down_sync(kFull, loc[v], off);
+    const double oc = __shfl_down_sync(kFull, bc, off);
+    const long long oi = __shfl_down_sync(kFull, bi, off);
+    if (better(oc, oi, bc, bi)) {
+      bc = oc;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int v = 0; v < 8; v++) wsum[warp][v] = loc[v];
+    wcost[warp] = bc;
+    widx[warp] = bi;
+  }
   __syncthreads();
   if (tid == 0) {
-    for (int j = 1; j < (int)blockDim.x; j++)
-      if (better(scost[j], sidx[j], bc, bi)) {
-        bc = scost[j];
-        bi = sidx[j];
+    unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < 8; w++) {
+      for (int v = 0; v < 8; v++) cnt[v] += wsum[w][v];
+      if (w > 0 && better(wcost[w], widx[w], bc, bi)) {
+        bc = wcost[w];
+        bi = widx[w];
       }
+    }
     for (int v = 0; v < 4; v++) {
       out->traj[v] = cnt[v];
       out->pair[v] = cnt[4 + v];
@@ -894,9 +912,12 @@ struct FeasArgs {
 // Reset()/SetInitialState() (SingleAxisTrajectory.cpp:133-158): a driver that reuses ONE object for a batch
 // (ForestPerformanceEval.cpp:177-209) evaluates every candidate of the batch with the peak times of the first
 // candidate that reached GetMinMaxAcc on that axis. One thread per group start walks its group in order until all
-// three axes are initialised (normally the first candidate) and writes the group's peak times for every member.
+// three axes are initialised (normally the first candidate) and writes the group's peak times to the group's ANCHOR
+// slots: its first member and every kAnchorStep-th after it (anchor[q] = 1). A member finds its group's values by walking
+// back to the nearest anchor (k_feas, at most kAnchorStep - 1 steps) -- 6 stores per group instead of 6 per member.
+constexpr int kAnchorStep = 1024;
 __global__ void __launch_bounds__(128) k_feas_group_peaks(const CheckParams p, const FeasArgs fa, const long long* group,
-                                                          double* peaks /* 6 rows x n */) {
+                                                          double* peaks /* 6 rows x n */, uint8_t* anchor /* n, zeroed */) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     if (i > 0 && group[i] == group[i - 1]) continue;
     bool init[3] = {false, false, false};
@@ -927,12 +948,14 @@ __global__ void __launch_bounds__(128) k_feas_group_peaks(const CheckParams p, c
           pk[k][1] = own[k][1];
         }
     }
-    for (long long q = i; q < j; q++)
+    for (long long q = i; q < j; q += kAnchorStep) {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         peaks[(2 * k) * p.n + q] = pk[k][0];
         peaks[(2 * k + 1) * p.n + q] = pk[k][1];
       }
+      anchor[q] = 1;
+    }
   }
 }
 
@@ -950,7 +973,7 @@ constexpr int kFeasRows = 32;  // per queued candidate: 3 x (a0, alpha, beta, ga
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const FeasArgs fa, const double* peaks, uint8_t* result,
                                                     uint8_t* verdict, int* first, int refill, long long* list,
-                                                    unsigned long long* n_list) {
+                                                    unsigned long long* n_list, const uint8_t* anchor) {
   extern __shared__ __align__(16) double feas_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -998,9 +1021,11 @@ __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const F
           AxisState nx[3];
           double Tf = 0.0;
           feas_axes(p, my < p.n ? my : p.n - 1, nx, Tf);
-          if (peaks && my < p.n) {
+          if (peaks && my < p.n) {  // the generator object's cached peak times: at the group's nearest anchor
+            long long at = my;
+            while (!anchor[at]) at--;
 #pragma unroll
-            for (int k = 0; k < 3; k++) nx[k].pk0 = peaks[(2 * k) * p.n + my], nx[k].pk1 = peaks[(2 * k + 1) * p.n + my];
+            for (int k = 0; k < 3; k++) nx[k].pk0 = peaks[(2 * k) * p.n + at], nx[k].pk1 = peaks[(2 * k + 1) * p.n + at];
           }
           double* e = queue + lane;  // slot = lane; slots [0, made) are valid
 #pragma unroll
@@ -1315,9 +1340,12 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
   for (int k = 0; k < 3; k++) fa.grav[k] = grav[k];
   fa.fmin = fmin, fa.fmax = fmax, fa.wmax = wmax, fa.min_t = min_t;
   const int grid = (int)((p.n + 127) / 128 < sm_count() * 16 ? (p.n + 127) / 128 : sm_count() * 16);
+  uint8_t* anchor = group ? reinterpret_cast<uint8_t*>(peaks + 6 * p.n) : nullptr;  // the caller's buffer holds 6 n doubles + n bytes
   if (group) {
-    k_feas_group_peaks<<<grid, 128, 0, s>>>(p, fa, group, peaks);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaMemsetAsync(anchor, 0, (size_t)p.n, s);
+    if (e != cudaSuccess) return e;
+    k_feas_group_peaks<<<grid, 128, 0, s>>>(p, fa, group, peaks, anchor);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
@@ -1346,7 +1374,7 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
     if (e != cudaSuccess) return e;
   }
   void* args[] = {(void*)&p, (void*)&fa, (void*)&pk, (void*)&result, (void*)&verdict, (void*)&first, (void*)&refill, (void*)&list,
-                  (void*)&n_list};
+                  (void*)&n_list, (void*)&anchor};
   return cudaLaunchKernel(fn, dim3(pgrid), dim3(128), args, smem, s);
 }
 

@@ -116,7 +116,7 @@ const char* pool_kernel_name(bool moving);
 
 cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, int np, uint8_t* verdict, uint8_t* matrix,
                           cudaStream_t s);
-// group may be null; peaks: scratch of 6*n doubles, needed when group is given
+// group may be null; peaks: scratch of 6*n doubles + n bytes, needed when group is given
 cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], double fmin, double fmax, double wmax,
                                double min_t, const long long* group, double* peaks, uint8_t* result, uint8_t* verdict,
                                int* first, long long* list /* accepted candidates, may be null */, unsigned long long* n_list,
