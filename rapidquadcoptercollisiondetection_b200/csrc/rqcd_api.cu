@@ -488,10 +488,10 @@ int run_host_pipeline(rqcd_ctx* ctx, CheckCall& cc, const rqcd_out* out, long lo
   return RQCD_OK;
 }
 
-// RQCD_F_FRAGILE: after the base launch, k_fragile walks every pair's recursion in lockstep with four copies whose
-// transcendental outputs (the cubic's cos / sin pair, Cardano's cube root) are moved by +-eta, once per probe magnitude
-// (RQCD_FRAGILE_LOG2, default 2^-50 and 2^-46: ~8 and ~130 ulp, where two conforming math libraries differ by one or
-// two). A pair whose copies do not take the same decisions in every section is marked (see k_fragile).
+// RQCD_F_FRAGILE: after the base launch, k_fragile walks every pair's recursion in lockstep with eight copies whose
+// transcendental outputs (the cubic's three cosines, Cardano's cube root) are moved by +-eta, once per probe magnitude
+// (RQCD_FRAGILE_LOG2, default 2^-50: ~8 ulp, where two conforming math libraries differ by one or two), and marks the
+// pairs with a sign decision that is not pinned (see k_fragile).
 int run_fragile_probes(rqcd_ctx* ctx, CheckCall& cc, const OutStage& o, long long n, uint8_t* d_fragile) {
   RQCD_CU(cudaMemsetAsync(d_fragile, 0, (size_t)n, ctx->stream));
   CheckParams q = cc.p;

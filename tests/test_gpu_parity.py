@@ -604,3 +604,21 @@ def test_fast_fma_flag_is_opt_in_and_close(ctx, oracle):
     ff = ctx.generate_check(c2, MIN_T, flags=abi.F_EARLY_EXIT | abi.F_FAST_FMA)
     assert int((fe["verdict"] != ff["verdict"]).sum()) <= 2
     assert pe["summary"]["pairs_checked"] == 1 << 14
+
+
+def test_performance_eval_end_to_end_on_the_device_at_full_size(ctx, golden_counts):
+    """test/PerformanceEval.cpp:117-182 as ONE call: the product package draws the driver's 15 571 728 trials (no oracle), the
+    input filter keeps exactly 10^7 of them -- the last one drawn among them, as in the driver's loop -- and their verdict
+    counts are the reference's checked-in 9 600 380 / 399 612 / 8 (data/PerformanceEval.txt:23-25)."""
+    bc, sph = W.c1_trials(golden_counts["c1_trials"])
+    ctx.set_input_filter()
+    try:
+        r = ctx.generate_check_pairwise(bc, sph, MIN_T)
+    finally:
+        ctx.set_input_filter(on=False)
+    accepted = r["input_feasibility"] == 0
+    assert int(accepted.sum()) == golden_counts["c1_n"] and accepted[-1]
+    assert r["summary"]["pairs_checked"] == golden_counts["c1_n"]
+    assert r["summary"]["traj_counts"][:3] == [golden_counts["c1_no_collision"], golden_counts["c1_collision"],
+                                              golden_counts["c1_indeterminable"]]
+    assert (r["verdict"][~accepted] == abi.NOT_CHECKED).all() and (r["verdict"][accepted] <= 2).all()
