@@ -573,6 +573,28 @@ def test_input_filter_reproduces_performance_eval(ctx, oracle):
     np.testing.assert_array_equal(f["first_obstacle"][k2], o2["first_obstacle"])
     assert (f["verdict"][~k2] == abi.NOT_CHECKED).all() and (f["first_obstacle"][~k2] == -2).all()
     assert f["summary"]["traj_counts"] == o2["summary"]["traj_counts"]
+    # a table long enough for the staged kernel (k_pool takes its work from the filter's accept list too), all pairs
+    specs = W.static_obstacles(77, 12, 12)
+    obs = abi.make_obstacles(specs)
+    ctx.set_obstacles(obs, len(specs))
+    b3 = W.synth_bc(78, 0, 20_011)
+    ctx.set_input_filter()
+    try:
+        g = ctx.generate_check(b3, MIN_T)
+        assert ctx.last_kernel_name().startswith("k_pool")
+    finally:
+        ctx.set_input_filter(on=False)
+    f3 = oracle.input_feasibility(b3)
+    np.testing.assert_array_equal(g["input_feasibility"], f3)
+    k3 = f3 == 0
+    o3 = oracle.generate_check(np.ascontiguousarray(b3[:, k3]), obs, len(specs), MIN_T, nthreads=8)
+    np.testing.assert_array_equal(g["verdict_matrix"][k3], o3["verdict_matrix"])
+    np.testing.assert_array_equal(g["verdict"][k3], o3["verdict"])
+    assert (g["verdict"][~k3] == abi.NOT_CHECKED).all()
+    assert g["summary"]["pair_counts"] == o3["summary"]["pair_counts"]
+    # the best candidate is named by its index in the caller's array, whatever order the accept list had
+    want_best = np.flatnonzero(k3)[o3["summary"]["best_index"]] if o3["summary"]["best_index"] >= 0 else -1
+    assert g["summary"]["best_index"] == want_best
 
 
 def test_fast_fma_flag_is_opt_in_and_close(ctx, oracle):

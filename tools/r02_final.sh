@@ -18,7 +18,7 @@ done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches_c3.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu_list.log 2>&1
 # full captures: the check kernel of every workload (second launch), k_feas
 for w in c3 c5 c4 c2 c1; do
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_pool|k_check' --launch-skip 1 --launch-count 1 -f -o $O/${TAG}_prof_$w python bench.py --workload $w --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > $O/${TAG}_ncu_full_$w.log 2>&1; tail -1 $O/${TAG}_ncu_full_$w.log
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'^(k_pool|k_check)$' --launch-skip 1 --launch-count 1 -f -o $O/${TAG}_prof_$w python bench.py --workload $w --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > $O/${TAG}_ncu_full_$w.log 2>&1; tail -1 $O/${TAG}_ncu_full_$w.log
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_feas --launch-skip 1 --launch-count 1 -f -o $O/${TAG}_prof_feas python tools/feas_bench.py 22 2 > $O/${TAG}_ncu_full_feas.log 2>&1; tail -1 $O/${TAG}_ncu_full_feas.log
 timeout 900 python tools/big_parity.py 23 64 > $O/${TAG}_big_parity_m64.log 2>&1; tail -1 $O/${TAG}_big_parity_m64.log
