@@ -404,13 +404,14 @@ int run_input_filter(rqcd_ctx* ctx, CheckCall& cc, const OutStage& o, long long 
   CheckParams q = cc.p;
   q.progress = nullptr;
   q.work_counter = ctx->d_counter;
-  // the accepted candidates as a dense list (any order): the check kernel then has no empty lanes for rejected ones
-  RQCD_CU(ensure(ctx->s_list, (size_t)n * 8 + 16));
+  // the accepted candidates as a dense ascending list: the check kernel then has no empty lanes for rejected ones
+  const size_t words = feasibility_list_words(n);
+  RQCD_CU(ensure(ctx->s_list, ((size_t)n + words) * 8));
   unsigned long long* n_list = (unsigned long long*)ctx->s_list.p;
-  long long* list = (long long*)ctx->s_list.p + 2;
+  long long* list = (long long*)ctx->s_list.p + words;
   RQCD_CU(launch_feasibility(q, L.gravity, L.fmin, L.fmax, L.wmax, L.min_time_section, nullptr, nullptr, d_feas, o.verdict,
                              cc.pairwise ? nullptr : o.first, list, n_list, ctx->stream));
-  ctx->launches++;
+  ctx->launches += 4;  // k_feas + the list's three
   cc.p.list = list;
   cc.p.n_list = n_list;
   cc.filter_mask = d_feas;

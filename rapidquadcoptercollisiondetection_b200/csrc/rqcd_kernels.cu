@@ -972,8 +972,7 @@ __global__ void __launch_bounds__(128) k_feas_group_peaks(const CheckParams p, c
 constexpr int kFeasRows = 32;  // per queued candidate: 3 x (a0, alpha, beta, gamma) + 3 x (pk0, pk1, AxisHoist) + Tf + index
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const FeasArgs fa, const double* peaks, uint8_t* result,
-                                                    uint8_t* verdict, int* first, int refill, long long* list,
-                                                    unsigned long long* n_list, const uint8_t* anchor) {
+                                                    uint8_t* verdict, int* first, int refill, const uint8_t* anchor) {
   extern __shared__ __align__(16) double feas_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -1055,8 +1054,6 @@ __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const F
       hz[k].tmax = hoist[(6 * k + 4) * 128], hz[k].jm = hoist[(6 * k + 5) * 128];
     }
     int res = feas_frame_sel(ax, hz, fa.grav, fa.fmin, fa.fmax, fa.wmax, t1, t2, fa.min_t);
-    bool done_now = false;
-    const long long done_idx = idx;
     if (have) {
       if (res == FEAS_SPLIT) {
         if (sp >= kMaxDepth) {
@@ -1078,21 +1075,87 @@ __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const F
           if (first) first[idx] = -2;
         }
         have = false;
-        done_now = true;
-      }
-    }
-    // the input filter's accept list: the candidates decided InputFeasible in this trip, appended with one atomic per warp
-    if (list) {
-      const bool acc = done_now && res == RQCD_INPUT_FEASIBLE_;
-      const unsigned am = __ballot_sync(kFull, acc);
-      if (am) {
-        unsigned long long at = 0;
-        if (lane == __ffs(am) - 1) at = atomicAdd(n_list, (unsigned long long)__popc(am));
-        at = __shfl_sync(kFull, at, __ffs(am) - 1);
-        if (acc) list[at + __popc(am & lt_mask)] = done_idx;
       }
     }
   }
+}
+
+// ---- the input filter's accept list: the indices i with result[i] == InputFeasible, ASCENDING (a stable compaction in
+// three small launches: per-chunk counts, their exclusive scan, the writes). The check kernel takes its work from this
+// list; ascending order keeps its reads of the boundary-condition rows as dense as the acceptance rate allows (a list
+// appended in completion order cost 1.8x the DRAM traffic).
+constexpr int kListChunk = 2048;  // candidates per block of 256 threads, 8 consecutive ones per thread
+__global__ void __launch_bounds__(256) k_list_count(const uint8_t* result, long long n, unsigned* chunk_count) {
+  const long long base = (long long)blockIdx.x * kListChunk + threadIdx.x * 8;
+  unsigned c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) c += (base + j < n && result[base + j] == RQCD_INPUT_FEASIBLE_) ? 1u : 0u;
+  c = __reduce_add_sync(kFull, c);
+  __shared__ unsigned ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) chunk_count[blockIdx.x] = ws[0] + ws[1] + ws[2] + ws[3] + ws[4] + ws[5] + ws[6] + ws[7];
+}
+// one block: chunk_count[0 .. nb) -> exclusive prefix sums in place (64-bit), total to *n_list
+__global__ void __launch_bounds__(1024) k_list_scan(const unsigned* chunk_count, unsigned long long* chunk_base, int nb,
+                                                    unsigned long long* n_list) {
+  __shared__ unsigned long long ws[32];
+  __shared__ unsigned long long carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0ull;
+  __syncthreads();
+  for (int b0 = 0; b0 < nb; b0 += 1024) {
+    const int b = b0 + threadIdx.x;
+    const unsigned long long v = b < nb ? chunk_count[b] : 0ull;
+    unsigned long long x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long y = __shfl_up_sync(kFull, x, off);
+      if (lane >= off) x += y;
+    }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = ws[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long y = __shfl_up_sync(kFull, w, off);
+        if (lane >= off) w += y;
+      }
+      ws[lane] = w;
+    }
+    __syncthreads();
+    const unsigned long long before = carry + (warp > 0 ? ws[warp - 1] : 0ull) + x - v;
+    if (b < nb) chunk_base[b] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_list = carry;
+}
+__global__ void __launch_bounds__(256) k_list_write(const uint8_t* result, long long n, const unsigned long long* chunk_base,
+                                                    long long* list) {
+  const long long base = (long long)blockIdx.x * kListChunk + threadIdx.x * 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned mask = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) mask |= (base + j < n && result[base + j] == RQCD_INPUT_FEASIBLE_) ? (1u << j) : 0u;
+  const unsigned c = __popc(mask);
+  unsigned x = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned y = __shfl_up_sync(kFull, x, off);
+    if (lane >= off) x += y;
+  }
+  __shared__ unsigned ws[8];
+  if (lane == 31) ws[warp] = x;
+  __syncthreads();
+  unsigned before = x - c;
+  for (int w = 0; w < warp; w++) before += ws[w];
+  long long* out = list + chunk_base[blockIdx.x] + before;
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    if ((mask >> j) & 1u) *out++ = base + j;
 }
 
 // ---- planner glue: stage code per candidate (rqcd_plan_stage). A non-zero stage doubles as k_check's skip mask.
@@ -1369,13 +1432,23 @@ cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], doubl
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const double* pk = group ? peaks : nullptr;
-  if (list) {
-    e = cudaMemsetAsync(n_list, 0, sizeof(unsigned long long), s);
-    if (e != cudaSuccess) return e;
-  }
-  void* args[] = {(void*)&p, (void*)&fa, (void*)&pk, (void*)&result, (void*)&verdict, (void*)&first, (void*)&refill, (void*)&list,
-                  (void*)&n_list, (void*)&anchor};
-  return cudaLaunchKernel(fn, dim3(pgrid), dim3(128), args, smem, s);
+  void* args[] = {(void*)&p, (void*)&fa, (void*)&pk, (void*)&result, (void*)&verdict, (void*)&first, (void*)&refill, (void*)&anchor};
+  e = cudaLaunchKernel(fn, dim3(pgrid), dim3(128), args, smem, s);
+  if (e != cudaSuccess || !list) return e;
+  // the accept list: n_list[0] = count, n_list[1 ..] = scratch (chunk bases, then chunk counts; see feasibility_list_words)
+  const int nb = (int)((p.n + kListChunk - 1) / kListChunk);
+  unsigned long long* chunk_base = n_list + 2;
+  unsigned* chunk_count = reinterpret_cast<unsigned*>(chunk_base + nb);
+  k_list_count<<<nb, 256, 0, s>>>(result, p.n, chunk_count);
+  k_list_scan<<<1, 1024, 0, s>>>(chunk_count, chunk_base, nb, n_list);
+  k_list_write<<<nb, 256, 0, s>>>(result, p.n, chunk_base, list);
+  return cudaGetLastError();
+}
+
+// 64-bit words of scratch launch_feasibility needs behind n_list for n candidates
+size_t feasibility_list_words(long long n) {
+  const size_t nb = (size_t)((n + kListChunk - 1) / kListChunk);
+  return 2 + nb + (nb + 1) / 2;
 }
 
 cudaError_t launch_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas, const uint8_t* plane_hit,

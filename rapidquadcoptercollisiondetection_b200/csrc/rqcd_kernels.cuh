@@ -119,8 +119,10 @@ cudaError_t launch_planes(const CheckParams& p, int mode, const double* planes, 
 // group may be null; peaks: scratch of 6*n doubles + n bytes, needed when group is given
 cudaError_t launch_feasibility(const CheckParams& p, const double grav[3], double fmin, double fmax, double wmax,
                                double min_t, const long long* group, double* peaks, uint8_t* result, uint8_t* verdict,
-                               int* first, long long* list /* accepted candidates, may be null */, unsigned long long* n_list,
+                               int* first, long long* list /* accepted candidates, ascending; may be null */,
+                               unsigned long long* n_list /* count, followed by feasibility_list_words(n) - 1 words of scratch */,
                                cudaStream_t s);
+size_t feasibility_list_words(long long n);
 // planner glue (rqcd_plan_best): stage codes, see rqcd_plan_stage in rqcd.h
 cudaError_t launch_plan_mask(long long n, const double* cost, double max_cost, const uint8_t* feas, const uint8_t* plane_hit,
                              uint8_t* stage, cudaStream_t s);
