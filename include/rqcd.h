@@ -185,17 +185,21 @@ typedef struct rqcd_out {
  * ratios of 1e3 and more) that ulp decides on which side of the tangent plane a computed critical point lands. With this
  * flag a second kernel (k_fragile) walks every pair's recursion again, in lockstep with eight copies whose transcendental
  * outputs are moved by +-2^-50 (the reference's three independent cosines in all sign patterns, Cardano's cube root
- * relatively), and asks of every SIGN decision of every section -- window vs minTimeSection, midpoint inside, the solver's
- * branches, each root against ts / mid / tf, the plane side of each test point -- whether it is farther from zero than
- * 4 x what the perturbation did to it + 8 ulps of the terms it is computed from (its own rounding noise; a plane-side
- * value on its noise floor is the signature of grazing contact). Decisions that cannot involve the transcendentals (the
- * first section's window / inside / end-point tests) are exempt. out->fragile[i] = 1 when a pair of trajectory i at or
- * before its first hit has such a decision; with a verdict_matrix, bit 7 of an entry marks the pair (the verdict stays in
- * bits 0..1). Verdicts are never changed. An unmarked verdict is the reference's on every conforming libm (tests: every
- * difference from the CPU reference on adversarial grazing populations is marked, with zero tolerance); a marked one
- * is a coin toss in the reference too. Monte Carlo batches: ~5e-6 of the pairs. Cost: a diagnostic, not a hot path --
- * one thread per pair, nine copies, the compiler's divisions: ~6e7 pairs/s (the check itself does 2e10). Tunables, read at rqcd_create: RQCD_FRAGILE_LOG2 (magnitudes,
- * default -50), RQCD_FRAGILE_MARGIN (4), RQCD_FRAGILE_FLOOR (8 ulps). rqcd_fragile_reasons says which decision it was. */
+ * relatively), and asks of every SIGN decision of every section that can change the outcome -- window vs minTimeSection,
+ * midpoint inside, the solver's branches, each root against ts / mid / tf, the plane side of each test point -- whether it
+ * is farther from zero than 4 x what the perturbation did to it + 8 ulps of the terms it is computed from (its own
+ * rounding noise; a plane-side value on its noise floor is the signature of grazing contact). Decisions that cannot
+ * involve the transcendentals (the first section's window / inside / end-point tests) are exempt, and so are positions
+ * and existence of test points that provably decide nothing (a free root next to a free end; the double root every
+ * rest-to-rest primitive has at t = Tf). out->fragile[i] = 1 when a pair of trajectory i at or before its first hit has an
+ * unpinned decision; with a verdict_matrix, bit 7 of an entry marks the pair (the verdict stays in bits 0..1). Verdicts
+ * are never changed. An unmarked verdict is the reference's on every conforming libm (tests: every difference from the
+ * CPU reference on adversarial grazing populations is marked, with zero tolerance); a marked one MAY be a coin toss in
+ * the reference too -- the mark is conservative: 0 of 4e6 Monte Carlo pairs, but 5 % of rest-to-rest primitives, whose
+ * double root makes the solver's choice of resolvent root a rounding matter although the test points come out the
+ * same. Cost: a diagnostic, not a hot path -- one thread per pair, nine copies, the compiler's divisions: ~6e7 pairs/s
+ * (the check itself does 2e10). Tunables, read at rqcd_create: RQCD_FRAGILE_LOG2 (magnitudes, default -50),
+ * RQCD_FRAGILE_MARGIN (4), RQCD_FRAGILE_FLOOR (8 ulps). rqcd_fragile_reasons says which decision it was. */
 #define RQCD_F_FRAGILE 0x4u
 
 /* Opt-in: run the check with the kernels' FMA-contracted build (the same sources compiled with -fmad=true instead of the
@@ -229,10 +233,11 @@ uint64_t rqcd_launch_count(const rqcd_ctx* ctx);
  * rqcd_plan_best launch on this context ("" before the first): what a profile of the call must show. */
 const char* rqcd_last_kernel_name(const rqcd_ctx* ctx);
 /* RQCD_F_FRAGILE diagnostics: how many pairs this context has marked so far, by the FIRST decision of the pair's recursion
- * that was not pinned: 0 window vs minTimeSection, 1 midpoint inside, 2 quartic or cubic, 3..10 the solver's branches
- * (trig / Cardano, |x2| < eps, choice of the resolvent root x2, |D| < eps x2, the two quadratics' discriminants),
- * 11 + 4 i + {0, 1, 2, 3}: sorted root i against ts / mid / tf and its plane side, 27 / 28 plane side of ts / tf,
- * 31 the perturbed copies disagreed on the section's result or root count. */
+ * that was needed and not pinned: 0 window vs minTimeSection, 1 midpoint inside, 2 quartic or cubic, 3..10 the solver's
+ * branches (3 trig / Cardano -- never needed --, 4 |x2| < eps, 5 / 6 choice of the resolvent root, 7 / 8 |D| < eps, 9 / 10 the
+ * two quadratic factors' discriminants), 11 + 4 j + {0, 1, 2, 3}: root j (by origin: 0, 1 the first factor's, 2, 3 the
+ * second's; the cubic's in 0..2) against ts / mid / tf and its plane side, 27 / 28 plane side of ts / tf, 31 the perturbed
+ * copies disagreed on the section's result, its children or the existence of roots. */
 int rqcd_fragile_reasons(rqcd_ctx* ctx, uint64_t counts[32]);
 
 /* Replaces constructing Sphere / RectPrism objects and the vector<shared_ptr<ConvexObj>> the drivers

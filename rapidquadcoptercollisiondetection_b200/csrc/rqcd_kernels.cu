@@ -508,31 +508,44 @@ __global__ void __launch_bounds__(256) k_finalize(const BlockPartial* parts, int
 // interval is bounded by a computed root, so the copies' sections drift apart by what the perturbation did to that root.
 //
 // A section is a list of SIGN DECISIONS (SectionProbe::q): window against minTimeSection, midpoint inside the obstacle,
-// quartic or cubic, the solver's own branches (SolverDecision), every sorted root against ts / mid / tf, the plane side
-// of every root inside the section and of both ends. Each comes with the magnitude of the terms it is the difference of
-// (SectionProbe::s): its own rounding noise is a few ulps of that. The copies act as a numerical derivative of each
-// quantity with respect to the transcendental outputs. A decision is PINNED when
+// quartic or cubic, the solver's own branches (SolverDecision), every root against ts / mid / tf, the plane side of every
+// root and of both ends. Each comes with the magnitude of the terms it is the difference of (SectionProbe::s): its own
+// rounding noise is a few ulps of that. The copies act as a numerical derivative of each quantity with respect to the
+// transcendental outputs. A decision is PINNED when
 //     |q(copy 0)| >= margin * max_v |q(copy v) - q(copy 0)| + floor_ulps * 2^-53 * s      (defaults: 4 and 8),
 // i.e. when it is farther from zero than what the perturbation did to it AND than the rounding noise of its own
 // evaluation (a root whose response to eta is below one ulp still moves by that ulp for some libm, and with it a
-// plane-side value that sits on its noise floor -- the signature of grazing contact). Decisions that do not depend on
-// the transcendentals at all -- the first section's window, inside test, degree test and end-point sides, and those of
-// children whose interval ends are exact midpoints -- are exempt: they are the reference's bits. A pair is MARKED at
-// the first section where a needed decision is not pinned (or the copies disagree on the root count or the section's
-// result); unmarked pairs take copy 0's decisions -- the shipped kernels' -- for every libm within eta.
+// plane-side value that sits on its noise floor -- the signature of grazing contact). Which decisions are NEEDED:
+//   * those that cannot involve the transcendentals -- the first section's window, inside test, degree test and end-point
+//     sides, and those of children whose interval ends are exact midpoints -- are exempt: they are the reference's bits;
+//   * a root is a test point: where it lies relative to ts / mid / tf only matters if the root can be on the obstacle side
+//     (its plane side is not pinned positive), or if the end it sits next to can (the child spawned by that end is bounded
+//     by its neighbour in the list, :166, :183). A root of a child section often IS the child's start: on a flat face the
+//     child's plane is the parent's;
+//   * roots are kept by ORIGIN (two per quadratic factor of the quartic), not by sorted position, so a factor whose
+//     discriminant changes sign under the perturbation -- an exact double root: every rest-to-rest primitive has one at
+//     t = Tf, for every plane -- does not shift the others. Such a factor's two roots appear or vanish at its double-root
+//     location -p/2; if the plane side THERE is pinned positive (and so are both ends'), test points that come and go
+//     there decide nothing: the discriminant's sign is then not needed, nor are that factor's roots;
+//   * the section's result and which children it has must be the same in all nine copies.
+// A pair is MARKED at the first section where a needed decision is not pinned; unmarked pairs take copy 0's decisions --
+// the shipped kernels' -- for every libm within eta.
 enum ProbeSlot {
   PQ_WINDOW = 0,  // (tf - ts) - minT                              (:93-96)
   PQ_INSIDE,      // sphere: r - |Xm - c|; prism: min_i (h_i - |q_i|)   (:89-92)
   PQ_QUART,       // |pc[0]| - 1e-6                                (:47, :116)
   PQ_SOLVER,      // SD_COUNT entries
-  PQ_ROOT = PQ_SOLVER + SD_COUNT,  // per sorted root: r - ts, r - mid, r - tf, plane side (4 x 4)
+  PQ_ROOT = PQ_SOLVER + SD_COUNT,  // per root by origin: r - ts, r - mid, r - tf, plane side (4 x 4)
   PQ_DTS = PQ_ROOT + 16, PQ_DTF,   // plane side of the section's ends
+  PQ_LOCA, PQ_LOCB,                // plane side at the double-root location of each quadratic factor
   PQ_COUNT
 };
 struct SectionProbe {
-  int sig;         // StepResult | has_hi << 4 | has_lo << 5 | root count << 8
-  unsigned need;   // which q[] entries decide this section
-  double t_next, lo_tf, mid;
+  int sig;          // StepResult | has_hi << 4 | has_lo << 5
+  unsigned need;    // which q[] entries decide this section (before the rules above drop some)
+  unsigned exists;  // bit j: root slot j holds a real root; bit 8: quartic (else cubic: slots 0..2)
+  double t_next, lo_tf, mid, ts, tf;
+  double loc[2];    // the double-root locations themselves
   double q[PQ_COUNT], s[PQ_COUNT];
 };
 // sum_d |n_d| (sum_k |c_kd| |t|^(5-k) + |point_d|): the magnitude of the terms of (X(t) - point) . n
@@ -543,7 +556,6 @@ RQCD_DEV double side_scale(const double (&c)[18], double t, V3 pp, V3 pn) {
   for (int k = 0; k < 6; k++) ax = ax * T + fabs(c[3 * k]), ay = ay * T + fabs(c[3 * k + 1]), az = az * T + fabs(c[3 * k + 2]);
   return fabs(pn.x) * (ax + fabs(pp.x)) + fabs(pn.y) * (ay + fabs(pp.y)) + fabs(pn.z) * (az + fabs(pp.z));
 }
-
 // `clean`: the section's ends do not depend on a computed root (the first section; children bounded by midpoints)
 template <class Obs>
 RQCD_DEV void probe_section(const double (&c)[18], double ts, double tf, const EndPoints ends, bool first, bool clean,
@@ -562,7 +574,18 @@ RQCD_DEV void probe_section(const double (&c)[18], double ts, double tf, const E
   V3 pp, pn;
   double pc[5], r[4];
   const int n = plane_and_roots(pm, c, obs, Xm, ctr, rad, prism, in_m, pp, pn, pc, r[0], r[1], r[2], r[3]);
-  sort_roots(n, r[0], r[1], r[2], r[3]);
+  const bool quart = fabs(pc[0]) > 1e-6;
+  // roots by origin: the quartic's from the solver's diagnostics, the cubic's as returned (x0; x1, x2 when real)
+  double ro[4];
+  unsigned ex;
+  if (quart) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) ro[j] = pm.pt.ro[j];
+    ex = (!(pm.pt.q[SD_DA] < 0.0) ? 3u : 0u) | (!(pm.pt.q[SD_DB] < 0.0) ? 12u : 0u) | 256u;
+  } else {
+    ro[0] = r[0], ro[1] = r[1], ro[2] = r[2], ro[3] = 0.0;
+    ex = n >= 2 ? 7u : 1u;
+  }
   Children ch;
   section_children(c, ts, tf, mid, pp, pn, pc, n, r[0], r[1], r[2], r[3], ends.amax(), !in_m, ch);
   int res = (ch.has_hi | ch.has_lo) ? STEP_CHILD : STEP_CLEAR;
@@ -570,7 +593,9 @@ RQCD_DEV void probe_section(const double (&c)[18], double ts, double tf, const E
   if (in_m) res = STEP_COLLISION;
   if (in_ends) res = STEP_COLLISION;
   o.sig = res | ((res == STEP_CHILD) ? ((ch.has_hi ? 16 : 0) | (ch.has_lo ? 32 : 0)) : 0);
-  o.t_next = ch.t_next, o.lo_tf = ch.lo_tf, o.mid = mid;
+  o.t_next = ch.t_next, o.lo_tf = ch.lo_tf, o.mid = mid, o.ts = ts, o.tf = tf;
+  o.loc[0] = pm.pt.loc[0], o.loc[1] = pm.pt.loc[1];
+  o.exists = 0;
 #pragma unroll
   for (int j = 0; j < PQ_COUNT; j++) o.q[j] = kNoDecision, o.s[j] = 0.0;
   o.q[PQ_WINDOW] = (tf - ts) - minT;
@@ -590,32 +615,45 @@ RQCD_DEV void probe_section(const double (&c)[18], double ts, double tf, const E
     if (!in_m) {
       if (!clean) need |= 1u << PQ_WINDOW;
       if (res != STEP_INDETERM) {
-        const bool quart = fabs(pc[0]) > 1e-6;
+        o.exists = ex;
         o.q[PQ_QUART] = fabs(pc[0]) - 1e-6;
         o.s[PQ_QUART] = 5.0 * ((fabs(pn.x * c[0]) + fabs(pn.y * c[1])) + fabs(pn.z * c[2]));
-        if (!clean) need |= (1u << PQ_QUART) | (1u << (PQ_SOLVER + SD_TRIG));
+        // (SD_TRIG is reported but never needed: r^2 < q^3 is decided before any transcendental is taken, and at
+        // r^2 = q^3 the two branches are continuations of each other -- a copy that takes the other one shows in the
+        // scatter of everything downstream)
+        if (!clean) need |= 1u << PQ_QUART;
         need |= 1u << (PQ_SOLVER + SD_X2);
         if (quart) need |= (((1u << SD_COUNT) - 1u) & ~(1u << SD_TRIG)) << PQ_SOLVER;
 #pragma unroll
         for (int j = 0; j < SD_COUNT; j++) o.q[PQ_SOLVER + j] = pm.pt.q[j], o.s[PQ_SOLVER + j] = pm.pt.qs[j];
-        o.sig |= n << 8;
+        // plane side D(t) = (X(t) - point) . n (:157-158, :180-181) and what one ulp of t does to it: D'(t) is the velocity
+        // polynomial the roots were computed from
+#define RQCD_PROBE_SIDE(slot, t_)                                                                                \
+  {                                                                                                             \
+    const double t = (t_);                                                                                      \
+    const double dv = fabs((((pc[0] * t + pc[1]) * t + pc[2]) * t + pc[3]) * t + pc[4]);                        \
+    o.q[slot] = dot(traj_value(c, t) - pp, pn);                                                                 \
+    o.s[slot] = side_scale(c, t, pp, pn) + dv * fabs(t);                                                        \
+  }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          if (i < n) {
-            o.q[PQ_ROOT + 4 * i + 0] = r[i] - ts, o.s[PQ_ROOT + 4 * i + 0] = fabs(r[i]) + fabs(ts);
-            o.q[PQ_ROOT + 4 * i + 1] = r[i] - mid, o.s[PQ_ROOT + 4 * i + 1] = fabs(r[i]) + fabs(mid);
-            o.q[PQ_ROOT + 4 * i + 2] = r[i] - tf, o.s[PQ_ROOT + 4 * i + 2] = fabs(r[i]) + fabs(tf);
-            need |= 7u << (PQ_ROOT + 4 * i);  // the caller drops comparisons that cannot matter, see k_fragile
-            o.q[PQ_ROOT + 4 * i + 3] = dot(traj_value(c, r[i]) - pp, pn);  // :157-158, :180-181
-            // + what one ulp of the root does: D'(t) = the velocity polynomial the root was computed from
-            const double t = r[i], dv = fabs((((pc[0] * t + pc[1]) * t + pc[2]) * t + pc[3]) * t + pc[4]);
-            o.s[PQ_ROOT + 4 * i + 3] = side_scale(c, t, pp, pn) + dv * fabs(t);
-            if (r[i] > ts && r[i] < tf) need |= 8u << (PQ_ROOT + 4 * i);
+          if ((ex >> i) & 1u) {
+            o.q[PQ_ROOT + 4 * i + 0] = ro[i] - ts, o.s[PQ_ROOT + 4 * i + 0] = fabs(ro[i]) + fabs(ts);
+            o.q[PQ_ROOT + 4 * i + 1] = ro[i] - mid, o.s[PQ_ROOT + 4 * i + 1] = fabs(ro[i]) + fabs(mid);
+            o.q[PQ_ROOT + 4 * i + 2] = ro[i] - tf, o.s[PQ_ROOT + 4 * i + 2] = fabs(ro[i]) + fabs(tf);
+            RQCD_PROBE_SIDE(PQ_ROOT + 4 * i + 3, ro[i])
+            need |= 7u << (PQ_ROOT + 4 * i);  // the caller drops comparisons that cannot matter
+            if (ro[i] > ts && ro[i] < tf) need |= 8u << (PQ_ROOT + 4 * i);
           }
         }
-        o.q[PQ_DTS] = dot(traj_value(c, ts) - pp, pn), o.s[PQ_DTS] = side_scale(c, ts, pp, pn);
-        o.q[PQ_DTF] = dot(traj_value(c, tf) - pp, pn), o.s[PQ_DTF] = side_scale(c, tf, pp, pn);
+        RQCD_PROBE_SIDE(PQ_DTS, ts)
+        RQCD_PROBE_SIDE(PQ_DTF, tf)
         if (!clean) need |= (1u << PQ_DTS) | (1u << PQ_DTF);
+        if (quart) {
+          RQCD_PROBE_SIDE(PQ_LOCA, pm.pt.loc[0])
+          RQCD_PROBE_SIDE(PQ_LOCB, pm.pt.loc[1])
+        }
+#undef RQCD_PROBE_SIDE
       }
     }
   }
@@ -625,7 +663,7 @@ RQCD_DEV void probe_section(const double (&c)[18], double ts, double tf, const E
 template <int MODE, bool MOVING, bool PAIRWISE>
 __global__ void __launch_bounds__(128) k_fragile(const CheckParams p, double eta, double margin, double floor_ulps, const int* first,
                                                  uint8_t* fragile, uint8_t* matrix, unsigned long long* why) {
-  static_assert(PQ_COUNT <= 32, "the need mask is one word");
+  static_assert(PQ_COUNT <= 31, "the need mask is one word; reason 31 is the copies' disagreement");
   constexpr int kCopies = 9;
   const int lane = threadIdx.x & 31;
   const long long m = PAIRWISE ? 1 : p.m, total = p.n * m;
@@ -676,6 +714,7 @@ __global__ void __launch_bounds__(128) k_fragile(const CheckParams p, double eta
     while (__any_sync(kFull, alive)) {
       SectionProbe base;
       double spread[PQ_COUNT], t_next[kCopies], lo_tf[kCopies];
+      unsigned ex_all = 0xffffffffu, ex_any = 0u;  // root slots that exist in every copy / in some copy
       bool differs = false;
 #pragma unroll 1
       for (int v = 0; v < kCopies; v++) {
@@ -687,6 +726,7 @@ __global__ void __launch_bounds__(128) k_fragile(const CheckParams p, double eta
         SectionProbe o;
         if (PAIRWISE) probe_section(c, ts[v], tf[v], ends, first_frame, clean, sph, p.min_t, pt, o);
         else probe_section(c, ts[v], tf[v], ends, first_frame, clean, obs, p.min_t, pt, o);
+        ex_all &= o.exists, ex_any |= o.exists;
         if (v == 0) {
           base = o;
 #pragma unroll
@@ -695,17 +735,20 @@ __global__ void __launch_bounds__(128) k_fragile(const CheckParams p, double eta
           differs = differs | (o.sig != base.sig);
 #pragma unroll
           for (int q = 0; q < PQ_COUNT; q++) {
+            // a root slot only compares where both copies have the root
+            const bool root_slot = q >= PQ_ROOT && q < PQ_ROOT + 16;
+            const bool both = !root_slot || (((o.exists & base.exists) >> ((q - PQ_ROOT) >> 2)) & 1u);
             const bool same = __double_as_longlong(o.q[q]) == __double_as_longlong(base.q[q]);
             const double d = fabs(o.q[q] - base.q[q]);
             // NaN differences (a NaN on one side only, inf - inf) count as unbounded
-            spread[q] = same ? spread[q] : ((d == d) ? fmax(spread[q], d) : __longlong_as_double(0x7ff0000000000000ll));
+            if (both && !same) spread[q] = (d == d) ? fmax(spread[q], d) : __longlong_as_double(0x7ff0000000000000ll);
           }
         }
         t_next[v] = o.t_next, lo_tf[v] = o.lo_tf;
       }
       first_frame = false;
       if (alive) {
-        int reason = differs ? 31 : -1;  // 31: the copies disagree on the section's result or root count
+        int reason = differs ? 31 : -1;  // 31: the copies disagree on the section's result or its children
         unsigned pinned = 0;
 #pragma unroll
         for (int q = 0; q < PQ_COUNT; q++) {
@@ -715,19 +758,70 @@ __global__ void __launch_bounds__(128) k_fragile(const CheckParams p, double eta
           const bool ok = shared_nan || fabs(base.q[q]) >= margin * spread[q] + floor_ulps * 1.1102230246251565e-16 * base.s[q];
           pinned |= ok ? (1u << q) : 0u;
         }
-        // Where a root lies relative to ts / mid / tf only matters if the root can be on the obstacle side, or if the end
-        // it sits next to can (the child spawned by that end is bounded by its neighbour in the list, :166, :183). A root
-        // of a child section often IS the child's start: on a flat face the child's plane is the parent's.
         unsigned need = base.need;
+        bool conflict = false;
         {
-          const bool ts_free = (clean || ((pinned >> PQ_DTS) & 1u)) && base.q[PQ_DTS] > 0.0;
-          const bool tf_free = (clean || ((pinned >> PQ_DTF) & 1u)) && base.q[PQ_DTF] > 0.0;
+          // pinned sign of a plane-side value: +1 free side, -1 obstacle side, 0 not pinned (a clean section's ends are the
+          // reference's own bits: pinned by construction)
+          auto side = [&](int slot, bool exact) -> int {
+            if (!(exact || ((pinned >> slot) & 1u))) return 0;
+            return base.q[slot] > 0.0 ? 1 : (base.q[slot] <= 0.0 ? -1 : 0);
+          };
+          const int s_ts = side(PQ_DTS, clean), s_tf = side(PQ_DTF, clean);
+          const bool quartic = (base.exists >> 8) & 1u;
+          int s_root[4];
 #pragma unroll
           for (int r_ = 0; r_ < 4; r_++) {
             const int b = PQ_ROOT + 4 * r_;
-            const bool root_free = ((pinned >> (b + 3)) & 1u) && base.q[b + 3] > 0.0;
-            const unsigned drop = ((ts_free ? 1u : 0u) | 2u | (tf_free ? 4u : 0u)) << b;
-            if (root_free) need &= ~drop;
+            s_root[r_] = ((base.exists >> r_) & 1u) ? side(b + 3, false) : 0;
+            // where the root lies relative to an end does not matter when both are robustly on the same side of the plane
+            // (whichever of the two is met first spawns the same child); relative to mid only when the root is free
+            unsigned drop = 0;
+            if (s_root[r_] != 0 && s_root[r_] == s_ts) drop |= 1u;
+            if (s_root[r_] > 0) drop |= 2u;
+            if (s_root[r_] != 0 && s_root[r_] == s_tf) drop |= 4u;
+            need &= ~(drop << b);
+          }
+          if (quartic) {
+            // a quadratic factor whose discriminant is not pinned: its two roots come and go at the double-root location
+            const double width = base.tf - base.ts;
+#pragma unroll
+            for (int f = 0; f < 2; f++) {
+              const int dslot = PQ_SOLVER + (f == 0 ? SD_DA : SD_DB), lslot = f == 0 ? PQ_LOCA : PQ_LOCB;
+              const unsigned two = 3u << (2 * f);
+              if (!((pinned >> dslot) & 1u)) {
+                const double x = base.loc[f], near = 1e-5 * (width + fabs(x));
+                const int s_loc = side(lslot, false);
+                const bool own_ok = (!((base.exists >> (2 * f)) & 1u) || s_root[2 * f] == s_loc) &&
+                                    (!((base.exists >> (2 * f + 1)) & 1u) || s_root[2 * f + 1] == s_loc);
+                bool harmless = false;
+                if (x < base.ts - near || x > base.tf + near) {
+                  harmless = true;  // out of the section whether they exist or not
+                } else if (fabs(x - base.tf) <= near) {
+                  harmless = s_loc != 0 && s_loc == s_tf && own_ok;  // next to tf, on tf's side of the plane
+                } else if (fabs(x - base.ts) <= near) {
+                  harmless = s_loc != 0 && s_loc == s_ts && own_ok;
+                } else if (fabs(x - base.mid) > near) {
+                  // inside one half: free test points that come and go decide nothing as long as no point of that half's
+                  // list can spawn a child bounded by them
+                  const bool high = x > base.mid;
+                  bool others_free = high ? (s_tf > 0) : (s_ts > 0);
+#pragma unroll
+                  for (int r_ = 0; r_ < 4; r_++) {
+                    if (!((base.exists >> r_) & 1u) || (r_ >> 1) == f) continue;
+                    const double rv = base.q[PQ_ROOT + 4 * r_ + 1];  // root - mid
+                    const bool same_half = high ? !(rv < -near) : !(rv > near);
+                    if (same_half && s_root[r_] <= 0) others_free = false;
+                  }
+                  harmless = s_loc > 0 && own_ok && others_free;
+                }
+                if (harmless) need &= ~((1u << dslot) | (0xffu << (PQ_ROOT + 8 * f)));
+              } else if (((ex_all ^ ex_any) & two) != 0) {
+                conflict = true;  // pinned discriminant, yet the copies disagree on the roots' existence
+              }
+            }
+          } else if ((ex_all ^ ex_any) & 7u) {
+            conflict = true;  // cubic: the copies disagree on the number of real roots
           }
         }
 #pragma unroll
@@ -736,6 +830,10 @@ __global__ void __launch_bounds__(128) k_fragile(const CheckParams p, double eta
             differs = true;
             reason = reason < 0 ? q : reason;
           }
+        if (conflict) {
+          differs = true;
+          reason = reason < 0 ? 31 : reason;
+        }
         const int res = base.sig & 7;
         if (differs) {
           frag = true;
@@ -743,9 +841,14 @@ __global__ void __launch_bounds__(128) k_fragile(const CheckParams p, double eta
           if (why) {
             const unsigned long long seen = atomicAdd(why + reason, 1ull);
 #ifdef RQCD_FRAGILE_DEBUG
-            if (seen < 3 && reason < PQ_COUNT)
-              printf("fragile i %lld k %d reason %d q %.17g spread %.3g scale %.3g ts %.17g tf %.17g sig %x depth %d clean %d\n", i, k, reason,
-                     base.q[reason], spread[reason], base.s[reason], ts[0], tf[0], base.sig, sp, (int)clean);
+            if (seen < 4 && reason < PQ_COUNT)
+              printf("fragile i %lld k %d reason %d q %.6g spread %.3g scale %.3g | ts %.17g tf %.17g sig %x sp %d clean %d ex %x exall %x exany %x | "
+                     "Dts %.3g(%d) Dtf %.3g(%d) locA %.17g D %.3g sp %.3g s %.3g (%d) locB D %.3g (%d) | roots %.17g %.17g %.17g %.17g | Droot %.3g %.3g %.3g %.3g pinned %x\n",
+                     i, k, reason, base.q[reason], spread[reason], base.s[reason], ts[0], tf[0], base.sig, sp, (int)clean, base.exists, ex_all, ex_any,
+                     base.q[PQ_DTS], (int)((pinned >> PQ_DTS) & 1), base.q[PQ_DTF], (int)((pinned >> PQ_DTF) & 1), base.q[PQ_ROOT + 2] + tf[0],
+                     base.q[PQ_LOCA], spread[PQ_LOCA], base.s[PQ_LOCA], (int)((pinned >> PQ_LOCA) & 1), base.q[PQ_LOCB], (int)((pinned >> PQ_LOCB) & 1),
+                     base.q[PQ_ROOT + 2] + tf[0], base.q[PQ_ROOT + 6] + tf[0], base.q[PQ_ROOT + 10] + tf[0], base.q[PQ_ROOT + 14] + tf[0],
+                     base.q[PQ_ROOT + 3], base.q[PQ_ROOT + 7], base.q[PQ_ROOT + 11], base.q[PQ_ROOT + 15], pinned);
 #else
             (void)seen;
 #endif
