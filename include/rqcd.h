@@ -195,7 +195,7 @@ typedef struct rqcd_out {
  * unpinned decision; with a verdict_matrix, bit 7 of an entry marks the pair (the verdict stays in bits 0..1). Verdicts
  * are never changed. An unmarked verdict is the reference's on every conforming libm (tests: every difference from the
  * CPU reference on adversarial grazing populations is marked, with zero tolerance); a marked one MAY be a coin toss in
- * the reference too -- the mark is conservative: 0 of 4e6 Monte Carlo pairs, but 5 % of rest-to-rest primitives, whose
+ * the reference too -- the mark is conservative: 0 of 4e6 Monte Carlo pairs, but 4 % of rest-to-rest primitives, whose
  * double root makes the solver's choice of resolvent root a rounding matter although the test points come out the
  * same. Cost: a diagnostic, not a hot path -- one thread per pair, nine copies, the compiler's divisions: ~6e7 pairs/s
  * (the check itself does 2e10). Tunables, read at rqcd_create: RQCD_FRAGILE_LOG2 (magnitudes, default -50),

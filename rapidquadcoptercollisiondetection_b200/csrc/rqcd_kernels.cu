@@ -622,8 +622,9 @@ RQCD_DEV void probe_section(const double (&c)[18], double ts, double tf, const E
         // r^2 = q^3 the two branches are continuations of each other -- a copy that takes the other one shows in the
         // scatter of everything downstream)
         if (!clean) need |= 1u << PQ_QUART;
-        need |= 1u << (PQ_SOLVER + SD_X2);
-        if (quart) need |= (((1u << SD_COUNT) - 1u) & ~(1u << SD_TRIG)) << PQ_SOLVER;
+        // (a quartic whose resolvent's single root dominates takes it whatever |x2| < eps says, see Perturb::x2_alt)
+        if (!(quart && pm.pt.x2_alt > 0.0)) need |= 1u << (PQ_SOLVER + SD_X2);
+        if (quart) need |= (((1u << SD_COUNT) - 1u) & ~((1u << SD_TRIG) | (1u << SD_X2))) << PQ_SOLVER;
 #pragma unroll
         for (int j = 0; j < SD_COUNT; j++) o.q[PQ_SOLVER + j] = pm.pt.q[j], o.s[PQ_SOLVER + j] = pm.pt.qs[j];
         // plane side D(t) = (X(t) - point) . n (:157-158, :180-181) and what one ulp of t does to it: D'(t) is the velocity
