@@ -1092,6 +1092,7 @@ __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const F
   double t1 = 0.0, t2 = 0.0;
   long long idx = -1;
   bool have = false, exhausted = false;
+  const FeasLimits lim = feas_limits(fa.fmin, fa.fmax, fa.wmax);
   for (;;) {
     unsigned idle = __ballot_sync(kFull, !have);
     if (__popc(idle) >= refill || idle == kFull) {
@@ -1157,7 +1158,10 @@ __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const F
       hz[k].ap0 = hoist[(6 * k + 2) * 128], hz[k].ap1 = hoist[(6 * k + 3) * 128];
       hz[k].tmax = hoist[(6 * k + 4) * 128], hz[k].jm = hoist[(6 * k + 5) * 128];
     }
-    int res = feas_frame_sel(ax, hz, fa.grav, fa.fmin, fa.fmax, fa.wmax, t1, t2, fa.min_t);
+    // the section on squares (feas_frame_sq); the roots themselves only where a comparison is within the roundings
+    bool open = false;
+    int res = feas_frame_sq(ax, hz, fa.grav, lim, fa.fmax, fa.wmax, t1, t2, fa.min_t, open);
+    if (!warp_all(!have | (lim.ok & !open))) res = feas_frame_sel(ax, hz, fa.grav, fa.fmin, fa.fmax, fa.wmax, t1, t2, fa.min_t);
     if (have) {
       if (res == FEAS_SPLIT) {
         if (sp >= kMaxDepth) {

@@ -73,3 +73,32 @@ def test_sphere_inside_filter_equals_the_rounded_root():
     inside, outside = d < lo, d > hi
     assert inside.sum() > 0.1 * n and outside.sum() > 0.1 * n and (~inside & ~outside).sum() > 0.1 * n
     assert np.all(literal[inside]) and not np.any(literal[outside])
+
+
+def test_feasibility_section_comparisons_on_squares():
+    """feas_frame_sq (rqcd_device.cuh): every root of a CheckInputFeasibilitySection is only compared with a limit
+    (RapidTrajectoryGenerator.cpp:85-147); the kernel decides on the squares when they are apart by more than the
+    roundings. Here: whenever the squares claim certainty, the literal comparison of the rounded root agrees."""
+    rng = np.random.default_rng(9)
+    n = 2_000_000
+    A = np.concatenate([np.full(n // 2, 5.0), 10.0 ** rng.uniform(-3, 3, n - n // 2)])  # fminA = 5 and generic limits
+    rel = rng.choice([0.0, 1e-16, 2e-16, 4e-16, 8e-16, 1.2e-15, 2e-15, 1e-12, 0.3], size=n) * rng.choice([-1.0, 1.0], size=n)
+    root = A * (1.0 + rel)
+    d = root * root * (1.0 + rng.choice([0.0, 1.1e-16, -1.1e-16, 2.2e-16], size=n))  # the squared quantity, around A^2
+    a2 = A * A
+    lo, hi = a2 * (1.0 - 1e-15), a2 * (1.0 + 1e-15)
+    f = np.sqrt(d)
+    below, above = d < lo, d > hi
+    assert below.sum() > 0.1 * n and above.sum() > 0.1 * n and (~below & ~above).sum() > 0.1 * n
+    assert np.all(f[below] < A[below]) and np.all(f[above] > A[above])
+    # the rate bound: sqrt(j / fminSqr) > wmaxA decided by j against wmaxA^2 fminSqr (1 -+ 4e-15)
+    W = np.concatenate([np.full(n // 2, 20.0), 10.0 ** rng.uniform(-2, 3, n - n // 2)])
+    fm = 10.0 ** rng.uniform(-6, 4, n)
+    rel = rng.choice([0.0, 1e-16, 4e-16, 1e-15, 2e-15, 3e-15, 5e-15, 1e-12, 0.3], size=n) * rng.choice([-1.0, 1.0], size=n)
+    j = (W * W) * fm * (1.0 + rel)
+    P = (W * W) * fm
+    plo, phi = P * (1.0 - 4e-15), P * (1.0 + 4e-15)
+    wq = np.sqrt(j / fm)
+    below, above = j < plo, j > phi
+    assert below.sum() > 0.1 * n and above.sum() > 0.1 * n and (~below & ~above).sum() > 0.1 * n
+    assert np.all(wq[below] < W[below]) and np.all(wq[above] > W[above])
