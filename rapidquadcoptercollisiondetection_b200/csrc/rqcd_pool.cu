@@ -141,9 +141,10 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
   constexpr int kWarps = T / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wbase = tid - lane;
   const int m = p.m, mp = p.mp;
-  double* tab = reinterpret_cast<double*>(smem_raw);
-  int* oflags = reinterpret_cast<int*>(tab + (size_t)p.stride * mp);
-  unsigned long long* wcnt = reinterpret_cast<unsigned long long*>(oflags + mp);      // [kWarps][8]
+  // Shared-memory layout: everything whose size only depends on T first, at compile-time offsets (a pointer that has to
+  // be recomputed from p.stride and p.mp at every use costs a dozen instructions under this kernel's register
+  // pressure), then the table, its flags and the end-point bits.
+  unsigned long long* wcnt = reinterpret_cast<unsigned long long*>(smem_raw);         // [kWarps][8]
   double* bcost = reinterpret_cast<double*>(wcnt + kWarps * 8);                       // [T]
   long long* bidx = reinterpret_cast<long long*>(bcost + T);                          // [T]
   double* rows = reinterpret_cast<double*>(bidx + T);                                 // [kPoolRows][T]
@@ -152,7 +153,12 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
   int* pool_ok = reinterpret_cast<int*>(pool_pl + kWarps * 6 * kPoolCap);             // [kWarps][kPoolCap]: owner << 16 | k
   int* queue = pool_ok + kWarps * kPoolCap;                                            // [kWarps][kQueueCap]: owner << 16 | k
   unsigned* res = reinterpret_cast<unsigned*>(queue + kWarps * kQueueCap);             // [T]: min (k << 2 | verdict)
-  unsigned* inbits = res + T;                                                         // [(mp + 31) / 32][T], static tables
+  static_assert((kWarps * 8 * 8 + T * 16 + kPoolRows * T * 8 + T * 8 + kWarps * kPoolCap * (6 * 8 + 4) + kWarps * kQueueCap * 4 + T * 4) %
+                        128 == 0,
+                "the table (TMA destination) starts on a 128-byte boundary");
+  double* tab = reinterpret_cast<double*>(res + T);                                   // [mp][stride]
+  int* oflags = reinterpret_cast<int*>(tab + (size_t)p.stride * mp);                  // [mp]
+  unsigned* inbits = reinterpret_cast<unsigned*>(oflags + mp);                        // [(mp + 31) / 32][T], static tables
   __shared__ __align__(8) uint64_t mbar;
 
   const uint32_t blob_bytes = (uint32_t)(((size_t)p.stride * mp) * 8 + (size_t)mp * 4);

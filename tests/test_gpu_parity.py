@@ -263,6 +263,34 @@ def test_input_feasibility_fresh_objects(ctx, oracle):
                                       oracle.input_feasibility(bc[:, :20_000], goal_mask=mask))
 
 
+def test_input_feasibility_limits_at_the_edge_of_a_comparison(ctx, oracle):
+    """k_feas decides a section's comparisons on squares (feas_frame_sq) and takes the roots themselves only when a
+    square is within the roundings of a limit's. Limits placed exactly ON a candidate's thrust at t = 0 (and one ulp to
+    either side), limits whose squares leave the certified range, zero and negative limits: the results stay the
+    reference's for every candidate of the batch."""
+    bc = W.synth_bc(62, 0, 8192)
+    g = np.array([0.0, 0.0, -9.81])
+    a0 = bc[abi.BC_A0:abi.BC_A0 + 3]
+    e = a0 - g[:, None]
+    thrust0 = np.sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2])  # RapidTrajectoryGenerator.hpp:192-194 at t = 0
+    cases = []
+    order = np.argsort(thrust0)
+    for q, which in ((0.03, "fmin"), (0.10, "fmin"), (0.90, "fmax"), (0.97, "fmax")):
+        f = float(thrust0[order[int(q * bc.shape[1])]])
+        for lim in (f, np.nextafter(f, 0.0), np.nextafter(f, np.inf)):
+            cases.append(dict(fmin=float(lim), fmax=30.0, wmax=20.0) if which == "fmin" else dict(fmin=5.0, fmax=float(lim), wmax=20.0))
+    cases += [dict(fmin=0.0, fmax=30.0, wmax=20.0), dict(fmin=-1.0, fmax=30.0, wmax=20.0), dict(fmin=5.0, fmax=30.0, wmax=1e200),
+              dict(fmin=5.0, fmax=30.0, wmax=1e-150), dict(fmin=1e-160, fmax=1e160, wmax=20.0),
+              dict(fmin=5.0, fmax=float("inf"), wmax=float("inf")), dict(fmin=5.0, fmax=30.0, wmax=0.0)]
+    seen = set()
+    for kw in cases:
+        got = ctx.input_feasibility(bc, **kw)
+        want = oracle.input_feasibility(bc, **kw)
+        np.testing.assert_array_equal(got, want, err_msg=str(kw))
+        seen |= set(np.unique(want).tolist())
+    assert seen >= {0, 1, 2, 3}
+
+
 def test_input_feasibility_forest_batches_match_reference_counts(ctx, oracle, vectors, forest_golden, golden_counts):
     """The Forest driver reuses one generator per batch (stale acceleration-peak cache): its own stream gives
     63.9533 % input feasible of 10^6 (data/ForestPerfEval.txt:28) and the inputFeas column of the CSV."""

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/sass_by_line.py REPORT.ncu-rep LIB.so [KERNEL_SUBSTR] -- attribute the executed warp-instructions of an ncu
+"""tools/sass_by_line.py REPORT.ncu-rep LIB.so [KERNEL_SUBSTR[&SUBSTR..]] -- attribute the executed warp-instructions of an ncu
 capture to source lines (nvdisasm -g line info of the SAME library build), split into FP64 / other, with the
 average number of active threads. Instructions are matched by their order inside the kernel."""
 import collections
@@ -24,7 +24,8 @@ def main():
     insts, cur, inside = [], ("?", 0), False
     for ln in dis:
         if ln.startswith(".text.") and ln.endswith(":"):
-            inside = sub in ln and "$" not in ln and not insts  # the first matching kernel, not its out-of-line helpers
+            # the first kernel whose name holds every '&'-separated part of KERNEL_SUBSTR, not its out-of-line helpers
+            inside = all(part in ln for part in sub.split("&")) and "$" not in ln and not insts
             continue
         if not inside:
             continue
