@@ -135,7 +135,9 @@ RQCD_DEV int plane_stage(const double (&c)[18], const TableObs& obs, V3 Xm, doub
   return r;
 }
 
-template <int MODE, bool MOVING, int T>
+// PLAIN: all pairs, no verdict matrix -- the common call; its early-exit tests and matrix stores are compiled out (the trip
+// loop does not fit the instruction cache, every branch it does not contain shows).
+template <int MODE, bool MOVING, int T, bool PLAIN>
 __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kWarps = T / 32;
@@ -185,7 +187,8 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
   double2 stack[kMaxDepth];  // the running task's parked low children {ts, lo_tf}
   unsigned long long avail = 0;
   bool exhausted = false;
-  const bool early = p.early_exit != 0;
+  const bool early = PLAIN ? false : (p.early_exit != 0);
+  uint8_t* const vmat = PLAIN ? nullptr : p.verdict_matrix;
 
   // with an accept list (input filter) the work items are positions of the list, else the candidates themselves
   const long long n_work = p.n_list ? (long long)*p.n_list : p.n;
@@ -296,11 +299,11 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
           const bool bit = (inbits[(k >> 5) * T + tid] >> (k & 31)) & 1u;
           const bool far = far_from_obstacle(xm0, hull_r, v3(rec[OF_CX], rec[OF_CY], rec[OF_CZ]), rec[OF_RBOUND]);
           if (push & bit) {
-            if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)1;
+            if (vmat) vmat[idx * (long long)m + k] = (uint8_t)1;
             n1++;
             atomicMin(&res[tid], ((unsigned)k << 2) | 1u);
           } else if (push & far) {
-            if (p.verdict_matrix) p.verdict_matrix[idx * (long long)m + k] = (uint8_t)0;
+            if (vmat) vmat[idx * (long long)m + k] = (uint8_t)0;
           }
           push = push & !bit & !far;
         }
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
           }
           const int v = (pre >= 0) ? pre : (active ? (r & 3) : -1);  // PS_SOLVE & 3 == 0: NoCollision until the task says otherwise
           if (v >= 0) {
-            if (p.verdict_matrix) p.verdict_matrix[idx_row[wbase + a_lane] * (long long)m + a_k] = (uint8_t)v;
+            if (vmat) vmat[idx_row[wbase + a_lane] * (long long)m + a_k] = (uint8_t)v;
             if (v != 0) {
               n1 += (v == 1), n2 += (v == 2);
               atomicMin(&res[wbase + a_lane], ((unsigned)a_k << 2) | (unsigned)v);
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_pool(const CheckParams p) {
         if (pv != 0) {
           n1 += (pv == 1), n2 += (pv == 2), n3 += (pv == 3);
           atomicMin(&res[wbase + owner], ((unsigned)kk << 2) | (unsigned)pv);
-          if (p.verdict_matrix) p.verdict_matrix[idx_row[wbase + owner] * (long long)m + kk] = (uint8_t)pv;
+          if (vmat) vmat[idx_row[wbase + owner] * (long long)m + kk] = (uint8_t)pv;
         }
       }
     }
@@ -530,18 +533,22 @@ __global__ void k_pool_init_constants() {
   g_pool_rcp_const[2] = rcp_refined(54.0);
 }
 
-template <int T>
+template <int T, bool PLAIN>
 const void* pool_fn(int mode, bool moving) {
   if (moving)
-    return mode == MODE_BC ? reinterpret_cast<const void*>(&k_pool<MODE_BC, true, T>)
-                           : reinterpret_cast<const void*>(&k_pool<MODE_COEFF, true, T>);
-  return mode == MODE_BC ? reinterpret_cast<const void*>(&k_pool<MODE_BC, false, T>)
-                         : reinterpret_cast<const void*>(&k_pool<MODE_COEFF, false, T>);
+    return mode == MODE_BC ? reinterpret_cast<const void*>(&k_pool<MODE_BC, true, T, PLAIN>)
+                           : reinterpret_cast<const void*>(&k_pool<MODE_COEFF, true, T, PLAIN>);
+  return mode == MODE_BC ? reinterpret_cast<const void*>(&k_pool<MODE_BC, false, T, PLAIN>)
+                         : reinterpret_cast<const void*>(&k_pool<MODE_COEFF, false, T, PLAIN>);
 }
+template <bool PLAIN>
 const void* pool_fn(int mode, bool moving, int threads) {
-  if (threads == 256) return pool_fn<256>(mode, moving);
-  if (threads == 384) return pool_fn<384>(mode, moving);
-  return pool_fn<512>(mode, moving);
+  if (threads == 256) return pool_fn<256, PLAIN>(mode, moving);
+  if (threads == 384) return pool_fn<384, PLAIN>(mode, moving);
+  return pool_fn<512, PLAIN>(mode, moving);
+}
+const void* pool_fn(int mode, bool moving, int threads, bool plain) {
+  return plain ? pool_fn<true>(mode, moving, threads) : pool_fn<false>(mode, moving, threads);
 }
 
 }  // namespace
@@ -583,19 +590,22 @@ int pool_threads(int mp, int stride, size_t smem_per_sm, size_t smem_per_block_m
 const char* pool_kernel_name(bool moving) { return moving ? "k_pool<moving>" : "k_pool<static>"; }
 
 cudaError_t pool_prepare(int mode, bool moving, int threads, size_t smem) {
-  return cudaFuncSetAttribute(pool_fn(mode, moving, threads), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(pool_fn(mode, moving, threads, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(pool_fn(mode, moving, threads, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 int pool_max_blocks_per_sm(int mode, bool moving, int threads, size_t smem) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pool_fn(mode, moving, threads), threads, smem) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pool_fn(mode, moving, threads, false), threads, smem) != cudaSuccess) return 0;
   return nb;
 }
 
 cudaError_t launch_pool(const CheckParams& p, int mode, bool moving, int threads, int grid, size_t smem, cudaStream_t s) {
   CheckParams q = p;
   void* args[] = {&q};
-  return cudaLaunchKernel(pool_fn(mode, moving, threads), dim3(grid), dim3(threads), args, smem, s);
+  const bool plain = p.verdict_matrix == nullptr && p.early_exit == 0;
+  return cudaLaunchKernel(pool_fn(mode, moving, threads, plain), dim3(grid), dim3(threads), args, smem, s);
 }
 
 }  // namespace rqcd
