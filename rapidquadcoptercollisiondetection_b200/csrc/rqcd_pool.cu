@@ -23,6 +23,7 @@
 // trajectory's verdict is the one of the lowest obstacle index (test/ForestPerformanceEval.cpp:216-225). With
 // RQCD_F_EARLY_EXIT tasks and first sections of obstacles behind a known hit are dropped, and the executed-pair counts
 // are the driver's (pairs up to and including the first hit).
+#define RQCD_OUTLINE_COLD  // the rare side paths of a section as calls, see rqcd_device.cuh
 #include "rqcd_kernel_util.cuh"
 
 namespace rqcd {
