@@ -1063,6 +1063,25 @@ __global__ void __launch_bounds__(128) k_feas_group_peaks(const CheckParams p, c
   }
 }
 
+// The section with its roots taken (feas_frame_sel), for the rare trips in which a lane's comparison is within the
+// roundings of a limit: out of line, so that the trip loop stays small; the per-candidate values come back from the
+// thread's shared-memory rows.
+struct FeasAxes {
+  double a0[3], a[3], b[3], g[3];
+};
+__device__ __noinline__ int feas_frame_literal(FeasAxes q, const double* hoist, FeasArgs fa, double t1, double t2) {
+  AxisState ax[3];
+  AxisHoist hz[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    ax[k].a0 = q.a0[k], ax[k].a = q.a[k], ax[k].b = q.b[k], ax[k].g = q.g[k];
+    ax[k].pk0 = hoist[(6 * k + 0) * 128], ax[k].pk1 = hoist[(6 * k + 1) * 128];
+    hz[k].ap0 = hoist[(6 * k + 2) * 128], hz[k].ap1 = hoist[(6 * k + 3) * 128];
+    hz[k].tmax = hoist[(6 * k + 4) * 128], hz[k].jm = hoist[(6 * k + 5) * 128];
+  }
+  return feas_frame_sel(ax, hz, fa.grav, fa.fmin, fa.fmax, fa.wmax, t1, t2, fa.min_t);
+}
+
 // k_feas: CheckInputFeasibility for every candidate. Persistent warps, lane owns candidate: every trip of the warp loop
 // runs ONE CheckInputFeasibilitySection per lane as one instruction stream (feas_frame_sel); a section that has to be
 // split continues with its first half and parks the second on the lane's stack (the reference's recursion order: the
@@ -1161,7 +1180,12 @@ __global__ void __launch_bounds__(128, MINB) k_feas(const CheckParams p, const F
     // the section on squares (feas_frame_sq); the roots themselves only where a comparison is within the roundings
     bool open = false;
     int res = feas_frame_sq(ax, hz, fa.grav, lim, fa.fmax, fa.wmax, t1, t2, fa.min_t, open);
-    if (!warp_all(!have | (lim.ok & !open))) res = feas_frame_sel(ax, hz, fa.grav, fa.fmin, fa.fmax, fa.wmax, t1, t2, fa.min_t);
+    if (!warp_all(!have | (lim.ok & !open))) {
+      FeasAxes q;
+#pragma unroll
+      for (int k = 0; k < 3; k++) q.a0[k] = ax[k].a0, q.a[k] = ax[k].a, q.b[k] = ax[k].b, q.g[k] = ax[k].g;
+      res = feas_frame_literal(q, hoist, fa, t1, t2);
+    }
     if (have) {
       if (res == FEAS_SPLIT) {
         if (sp >= kMaxDepth) {
