@@ -29,9 +29,12 @@
 //     shape; tables of 16+ obstacles run with free-running warps.
 //   * per-CTA partial verdict counts / best candidate, reduced in block order by k_finalize (deterministic).
 //
-// k_check_pool (further down) is the kernel of ONE shape -- all pairs against a static table of 16..100 obstacles
-// -- built around the first frame of a pair: first frames in obstacle order with X(mid) evaluated once per
-// trajectory, the pairs that need a recursion as tasks in a per-warp pool; same frame(), same verdicts.
+// k_check is the kernel of the PAIRWISE shape and of SHORT static tables (and of every shape with RQCD_POOL=0); obstacle
+// tables go to k_pool (rqcd_pool.cu: staged sections, certified solver skip, tasks decoupled from their owner lanes).
+// Same device functions, same verdicts. Staged sections were tried here too (PLANE / SOLVE trips per warp) and cost 20 %:
+// a lane that owns its trajectory idles while it waits for its kind of trip.
+// This file also holds k_feas (CheckInputFeasibility, sections decided on squares), the accept list of the input filter,
+// k_planes, k_generate, the solver unit kernels, k_fragile, k_finalize and the multi-GPU summary kernels.
 #include <cstdio>
 #include "rqcd_kernel_util.cuh"
 

@@ -23,6 +23,10 @@
 // trajectory's verdict is the one of the lowest obstacle index (test/ForestPerformanceEval.cpp:216-225). With
 // RQCD_F_EARLY_EXIT tasks and first sections of obstacles behind a known hit are dropped, and the executed-pair counts
 // are the driver's (pairs up to and including the first hit).
+// Instruction cache: the trip loop is ~30 KB of SASS against a 32 KB cache, and four warps per scheduler sit on different
+// trips. Everything that is not needed by the common call is kept out of it: the PLAIN variant compiles the early-exit
+// tests and verdict-matrix stores out, the rare side paths of a section are calls (RQCD_OUTLINE_COLD), the compiler's own
+// division / sqrt fallbacks are out-of-line functions. Each of these was worth 5-11 %.
 #define RQCD_OUTLINE_COLD  // the rare side paths of a section as calls, see rqcd_device.cuh
 #include "rqcd_kernel_util.cuh"
 
