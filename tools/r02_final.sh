@@ -25,3 +25,10 @@ timeout 900 python tools/big_parity.py 23 64 > $O/${TAG}_big_parity_m64.log 2>&1
 timeout 900 python tools/big_parity.py 22 256 > $O/${TAG}_big_parity_m256.log 2>&1; tail -1 $O/${TAG}_big_parity_m256.log
 timeout 900 python tools/big_parity.py 24 32 moving > $O/${TAG}_big_parity_moving.log 2>&1; tail -1 $O/${TAG}_big_parity_moving.log
 timeout 900 python tools/big_parity.py 25 5 forest > $O/${TAG}_big_parity_forest.log 2>&1; tail -1 $O/${TAG}_big_parity_forest.log
+# gpurun brings back at most 64 MiB of gpurun_out/: summarise the captures here (profiles/ of THIS copy), hand the summaries
+# back in gpurun_out/collected/, and keep only the c3 report itself
+python tools/r02_collect.py $TAG | tail -8
+mkdir -p $O/collected
+cp profiles/${TAG}_ncu_*.md profiles/ncu_traffic.json profiles/${TAG}_sass_kernels.txt $O/collected/
+rm -f $O/${TAG}_prof_c[1245].ncu-rep $O/${TAG}_prof_feas.ncu-rep
+du -sh $O
