@@ -102,3 +102,101 @@ def test_feasibility_section_comparisons_on_squares():
     below, above = j < plo, j > phi
     assert below.sum() > 0.1 * n and above.sum() > 0.1 * n and (~below & ~above).sum() > 0.1 * n
     assert np.all(wq[below] < W[below]) and np.all(wq[above] > W[above])
+
+
+def _feas_section_both_ways(rng, n):
+    """One CheckInputFeasibilitySection (RapidTrajectoryGenerator.cpp:74-147) on random axes and intervals, restated twice
+    in numpy: literally (roots taken, feas_frame_sel's expressions) and on squares (feas_frame_sq's). Returns
+    (literal result, squares result, open)."""
+    fminA, fmaxA, wmaxA, minT = 5.0, 30.0, 20.0, 0.002
+    grav = np.array([0.0, 0.0, -9.81])
+    Tf = rng.uniform(0.2, 4.0, n)
+    a0 = rng.uniform(-4, 4, (3, n))
+    al = rng.uniform(-4, 4, (3, n)) * 60 / Tf ** 3 * rng.choice([0.0, 0.3, 1.0], size=(3, n))
+    be = rng.uniform(-4, 4, (3, n)) * 24 / Tf ** 2 * rng.choice([0.0, 0.3, 1.0], size=(3, n))
+    ga = rng.uniform(-4, 4, (3, n)) * 6 / Tf * rng.choice([0.0, 0.3, 1.0], size=(3, n))
+    lo = rng.uniform(0, 1, n) * rng.choice([0.0, 1.0], size=n)
+    t1 = lo * Tf
+    t2 = t1 + (Tf - t1) * rng.choice([1.0, 0.5, 0.25, 1e-3, 1e-4], size=n)
+
+    def acc(k, t):  # SingleAxisTrajectory.hpp:56-58
+        return a0[k] + ga[k] * t + (1 / 2.0) * be[k] * t * t + (1 / 6.0) * al[k] * t * t * t
+
+    def jerk(k, t):  # :54
+        return ga[k] + be[k] * t + (1 / 2.0) * al[k] * t * t
+
+    with np.errstate(all="ignore"):
+        def thrust_sq(t):
+            e = [acc(k, t) - grav[k] for k in range(3)]
+            return e[0] * e[0] + e[1] * e[1] + e[2] * e[2]
+
+        d1, d2 = thrust_sq(t1), thrust_sq(t2)
+        fmin_sq = np.zeros(n)
+        fmax_sq = np.zeros(n)
+        jmax_sq = np.zeros(n)
+        axis_high = np.zeros(n, bool)
+        for k in range(3):
+            has = al[k] != 0.0
+            det = be[k] * be[k] - 2 * ga[k] * al[k]
+            sa = np.where(has, al[k], 1.0)
+            root = np.sqrt(np.where(det < 0, 0.0, det))
+            pk0 = np.where(has, np.where(det < 0, 0.0, (-be[k] + root) / sa), np.where(be[k] != 0, -ga[k] / np.where(be[k] != 0, be[k], 1.0), 0.0))
+            pk1 = np.where(has, np.where(det < 0, 0.0, (-be[k] - root) / sa), 0.0)
+            x1, x2 = acc(k, t1), acc(k, t2)
+            amin, amax = np.minimum(x1, x2), np.maximum(x1, x2)
+            for pk in (pk0, pk1):  # SingleAxisTrajectory.cpp:160-171
+                inside = ~(pk <= t1) & ~(pk >= t2)
+                ap = acc(k, pk)
+                amin = np.where(inside, np.minimum(amin, ap), amin)
+                amax = np.where(inside, np.maximum(amax, ap), amax)
+            v1, v2 = amin - grav[k], amax - grav[k]
+            axis_high |= np.maximum(v1 * v1, v2 * v2) > fmaxA * fmaxA
+            m = np.minimum(np.abs(v1), np.abs(v2))
+            fmin_sq += np.where(v1 * v2 < 0, 0.0, m * m)
+            M = np.maximum(np.abs(v1), np.abs(v2))
+            fmax_sq += M * M
+            j = np.maximum(jerk(k, t1) ** 2, jerk(k, t2) ** 2)  # :182-197
+            tmax = -be[k] / sa
+            jm = np.maximum(jerk(k, tmax) ** 2, j)
+            jmax_sq += np.where(has & (tmax > t1) & (tmax < t2), jm, j)
+        big = fmin_sq > 1e-6
+        SPLIT, OK, IND, HIGH, LOW = 100, 0, 1, 2, 3
+
+        def pick(split, f_gt_max, F_lt_min, e_lt_min, e_gt_max):
+            r = np.where(split, SPLIT, OK)
+            r = np.where(f_gt_max, HIGH, r)
+            r = np.where(F_lt_min, LOW, r)
+            r = np.where(axis_high, HIGH, r)
+            r = np.where(e_lt_min, LOW, r)
+            r = np.where(e_gt_max, HIGH, r)
+            return np.where(t2 - t1 < minT, IND, r)
+
+        # literal: the roots themselves
+        f1, f2, fmin, fmax = np.sqrt(d1), np.sqrt(d2), np.sqrt(fmin_sq), np.sqrt(fmax_sq)
+        wb = np.where(big, np.sqrt(jmax_sq / np.where(big, fmin_sq, 1.0)), 1.7976931348623157e308)
+        lit = pick((fmin < fminA) | (fmax > fmaxA) | (wb > wmaxA), fmin > fmaxA, fmax < fminA,
+                   np.minimum(f1, f2) < fminA, np.maximum(f1, f2) > fmaxA)
+        # on squares
+        a2, b2, w2 = fminA * fminA, fmaxA * fmaxA, wmaxA * wmaxA
+        lo_min, hi_min, lo_max, hi_max = a2 * (1 - 1e-15), a2 * (1 + 1e-15), b2 * (1 - 1e-15), b2 * (1 + 1e-15)
+        P = w2 * fmin_sq
+        plo, phi = P * (1 - 4e-15), P * (1 + 4e-15)
+
+        def und(x):
+            return (~(x < lo_min) & ~(x > hi_min)) | (~(x < lo_max) & ~(x > hi_max))
+
+        opened = und(d1) | und(d2) | und(fmin_sq) | und(fmax_sq) | (big & ~(jmax_sq < plo) & ~(jmax_sq > phi))
+        w_gt = np.where(big, jmax_sq > phi, 1.7976931348623157e308 > wmaxA)
+        sq = pick((fmin_sq < lo_min) | (fmax_sq > hi_max) | w_gt, fmin_sq > hi_max, fmax_sq < lo_min,
+                  (d1 < lo_min) | (d2 < lo_min), (d1 > hi_max) | (d2 > hi_max))
+    return lit, sq, opened
+
+
+def test_feasibility_section_on_squares_equals_the_literal_section():
+    """feas_frame_sq against feas_frame_sel, both restated in numpy, on 3e6 random sections (whole windows, halves, slivers
+    below minT, axes with vanishing alpha / beta / gamma): wherever the squares claim certainty the results agree, and
+    they claim it almost always."""
+    lit, sq, opened = _feas_section_both_ways(np.random.default_rng(10), 3_000_000)
+    assert opened.mean() < 1e-6
+    assert np.array_equal(lit[~opened], sq[~opened])
+    assert len(np.unique(lit)) == 5  # feasible, indeterminable, thrust high, thrust low and "split" all occur
